@@ -1,0 +1,260 @@
+// curve.cuh — NIST prime curves (a = -3) in Montgomery form: field policies and Jacobian group law.
+//
+// A curve policy C provides: N (limbs), field ops fmul/fsqr/fadd/fsub on canonical residues in
+// [0,p) (Montgomery form, R = 2^(32N)), scalar-field Montgomery product nmul, and constants.
+// Everything is thread-private and register resident; callers choose where points live.
+#pragma once
+#include "curve_constants.h"
+#include "mp.cuh"
+
+namespace sbv {
+
+// -------------------------------------------------------------------------------------------------
+// P-256: p = 2^256 - 2^224 + 2^192 + 2^96 - 1.  -p^-1 mod 2^64 = 1, so Montgomery reduction needs
+// no multiplications: per 64-bit step the quotient digit is the low limb pair itself and
+// q*p = q*2^256 - q*2^224 + q*2^192 + q*2^96 - q is four shifted adds.
+// -------------------------------------------------------------------------------------------------
+struct P256 {
+    static constexpr int N = 8;
+    static constexpr int BYTES = 32;
+    static constexpr uint32_t NINV = SBV_P256_NINV;
+
+    SBV_DEV static void get_p(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_P; mp_copy<8>(r, c); }
+    SBV_DEV static void get_n(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_N; mp_copy<8>(r, c); }
+    SBV_DEV static void get_one(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_ONE_P; mp_copy<8>(r, c); }
+    SBV_DEV static void get_rr_p(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_RR_P; mp_copy<8>(r, c); }
+    SBV_DEV static void get_b(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_B_MONT; mp_copy<8>(r, c); }
+    SBV_DEV static void get_gx(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_GX_MONT; mp_copy<8>(r, c); }
+    SBV_DEV static void get_gy(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_GY_MONT; mp_copy<8>(r, c); }
+    SBV_DEV static void get_rr_n(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_RR_N; mp_copy<8>(r, c); }
+    SBV_DEV static void get_one_n(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_ONE_N; mp_copy<8>(r, c); }
+    SBV_DEV static void get_p_minus_n(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_P_MINUS_N; mp_copy<8>(r, c); }
+    SBV_DEV static uint32_t p_minus_2_limb(int i) { const uint32_t c[8] = SBV_P256_P_MINUS_2; return c[i]; }
+    SBV_DEV static uint32_t n_minus_2_limb(int i) { const uint32_t c[8] = SBV_P256_N_MINUS_2; return c[i]; }
+
+    // T (16 limbs, < p*2^256) -> r = T * 2^-256 mod p, canonical
+    SBV_DEV static void redc(uint32_t (&r)[8], uint32_t (&T)[16]) {
+        uint32_t t16 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int b = 2 * k;
+            const uint32_t mlo = T[b], mhi = T[b + 1];
+            T[b + 3] = add_cc(T[b + 3], mlo);
+            T[b + 4] = addc_cc(T[b + 4], mhi);
+            T[b + 5] = addc_cc(T[b + 5], 0);
+            T[b + 6] = addc_cc(T[b + 6], mlo);
+            T[b + 7] = addc_cc(T[b + 7], mhi);
+            T[b + 8] = addc_cc(T[b + 8], mlo);
+            T[b + 9] = addc_cc(T[b + 9], mhi);
+#pragma unroll
+            for (int j = b + 10; j < 16; j++) T[j] = addc_cc(T[j], 0);
+            t16 = addc(t16, 0);
+            T[b + 7] = sub_cc(T[b + 7], mlo);
+            T[b + 8] = subc_cc(T[b + 8], mhi);
+#pragma unroll
+            for (int j = b + 9; j < 16; j++) T[j] = subc_cc(T[j], 0);
+            t16 = subc(t16, 0);
+        }
+        uint32_t hi[8], t[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) hi[i] = T[8 + i];
+        const uint32_t p[8] = SBV_P256_P;
+        uint32_t bw = mp_sub<8>(t, hi, p);
+        bool use_t = (t16 != 0) || (bw == 0);
+        mp_select<8>(r, use_t, t, hi);
+    }
+    SBV_DEV static void fmul(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+        uint32_t T[16];
+        mp_mul<8>(T, a, b);
+        redc(r, T);
+    }
+    SBV_DEV static void fsqr(uint32_t (&r)[8], const uint32_t (&a)[8]) { fmul(r, a, a); }
+    SBV_DEV static void fadd(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+        const uint32_t p[8] = SBV_P256_P;
+        mod_add<8>(r, a, b, p);
+    }
+    SBV_DEV static void fsub(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+        const uint32_t p[8] = SBV_P256_P;
+        mod_sub<8>(r, a, b, p);
+    }
+    SBV_DEV static void nmul(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+        const uint32_t n[8] = SBV_P256_N;
+        mont_mul_generic<8>(r, a, b, n, SBV_P256_NINV);
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// P-384: generic word-serial Montgomery for both fields (12 limbs).
+// -------------------------------------------------------------------------------------------------
+struct P384 {
+    static constexpr int N = 12;
+    static constexpr int BYTES = 48;
+
+    SBV_DEV static void get_p(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_P; mp_copy<12>(r, c); }
+    SBV_DEV static void get_n(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_N; mp_copy<12>(r, c); }
+    SBV_DEV static void get_one(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_ONE_P; mp_copy<12>(r, c); }
+    SBV_DEV static void get_rr_p(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_RR_P; mp_copy<12>(r, c); }
+    SBV_DEV static void get_b(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_B_MONT; mp_copy<12>(r, c); }
+    SBV_DEV static void get_gx(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_GX_MONT; mp_copy<12>(r, c); }
+    SBV_DEV static void get_gy(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_GY_MONT; mp_copy<12>(r, c); }
+    SBV_DEV static void get_rr_n(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_RR_N; mp_copy<12>(r, c); }
+    SBV_DEV static void get_one_n(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_ONE_N; mp_copy<12>(r, c); }
+    SBV_DEV static void get_p_minus_n(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_P_MINUS_N; mp_copy<12>(r, c); }
+    SBV_DEV static uint32_t p_minus_2_limb(int i) { const uint32_t c[12] = SBV_P384_P_MINUS_2; return c[i]; }
+    SBV_DEV static uint32_t n_minus_2_limb(int i) { const uint32_t c[12] = SBV_P384_N_MINUS_2; return c[i]; }
+
+    SBV_DEV static void fmul(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
+        const uint32_t p[12] = SBV_P384_P;
+        mont_mul_generic<12>(r, a, b, p, SBV_P384_PINV);
+    }
+    SBV_DEV static void fsqr(uint32_t (&r)[12], const uint32_t (&a)[12]) { fmul(r, a, a); }
+    SBV_DEV static void fadd(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
+        const uint32_t p[12] = SBV_P384_P;
+        mod_add<12>(r, a, b, p);
+    }
+    SBV_DEV static void fsub(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
+        const uint32_t p[12] = SBV_P384_P;
+        mod_sub<12>(r, a, b, p);
+    }
+    SBV_DEV static void nmul(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
+        const uint32_t n[12] = SBV_P384_N;
+        mont_mul_generic<12>(r, a, b, n, SBV_P384_NINV);
+    }
+};
+
+// -------------------------------------------------------------------------------------------------
+// Jacobian points (X, Y, Z) ~ (X/Z^2, Y/Z^3); Z == 0 is the point at infinity.
+// -------------------------------------------------------------------------------------------------
+template <class C>
+struct Jac {
+    uint32_t X[C::N], Y[C::N], Z[C::N];
+};
+
+// a = -3 doubling, 4M + 4S.  Infinity (Z = 0) maps to infinity; Y = 0 cannot occur (odd order).
+template <class C>
+SBV_DEV void pt_double(Jac<C> &P) {
+    constexpr int N = C::N;
+    uint32_t delta[N], gamma[N], beta[N], alpha[N], t1[N], t2[N];
+    C::fsqr(delta, P.Z);
+    C::fsqr(gamma, P.Y);
+    C::fmul(beta, P.X, gamma);
+    C::fsub(t1, P.X, delta);
+    C::fadd(t2, P.X, delta);
+    C::fmul(alpha, t1, t2);
+    C::fadd(t1, alpha, alpha);
+    C::fadd(alpha, t1, alpha);  // alpha = 3 (X - delta)(X + delta)
+    C::fmul(t1, P.Y, P.Z);
+    C::fadd(P.Z, t1, t1);       // Z3 = 2 Y Z
+    C::fadd(beta, beta, beta);
+    C::fadd(beta, beta, beta);  // 4 beta
+    C::fsqr(t1, alpha);
+    C::fadd(t2, beta, beta);    // 8 beta
+    C::fsub(P.X, t1, t2);       // X3 = alpha^2 - 8 beta
+    C::fsub(t1, beta, P.X);
+    C::fmul(t2, alpha, t1);
+    C::fsqr(t1, gamma);
+    C::fadd(t1, t1, t1);
+    C::fadd(t1, t1, t1);
+    C::fadd(t1, t1, t1);        // 8 gamma^2
+    C::fsub(P.Y, t2, t1);
+}
+
+// P += (x2, y2[, z2]).  AFFINE: z2 == 1 (mixed add, 8M+3S) else general (12M+4S).
+// `skip` leaves P unchanged (digit 0).  `neg` adds the negated point.  Handles every exceptional
+// case: P = inf -> result is the addend; P == addend -> doubling; P == -addend -> infinity (Z3 = 0).
+template <class C, bool AFFINE>
+SBV_DEV void pt_add(Jac<C> &P, const uint32_t (&x2)[C::N], const uint32_t (&y2_in)[C::N],
+                    const uint32_t (&z2)[C::N], bool neg, bool skip) {
+    constexpr int N = C::N;
+    uint32_t y2[N], zero[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) zero[i] = 0;
+    {
+        uint32_t ny[N];
+        C::fsub(ny, zero, y2_in);
+        mp_select<N>(y2, neg, ny, y2_in);
+    }
+    const bool p_inf = mp_is_zero<N>(P.Z);
+    uint32_t z1z1[N], u1[N], u2[N], s1[N], s2[N], h[N], r[N], t[N];
+    C::fsqr(z1z1, P.Z);
+    C::fmul(u2, x2, z1z1);
+    C::fmul(t, P.Z, z1z1);
+    C::fmul(s2, y2, t);
+    if (AFFINE) {
+        mp_copy<N>(u1, P.X);
+        mp_copy<N>(s1, P.Y);
+    } else {
+        uint32_t z2z2[N];
+        C::fsqr(z2z2, z2);
+        C::fmul(u1, P.X, z2z2);
+        C::fmul(t, z2, z2z2);
+        C::fmul(s1, P.Y, t);
+    }
+    C::fsub(h, u2, u1);
+    C::fsub(r, s2, s1);
+    const bool h0 = mp_is_zero<N>(h), r0 = mp_is_zero<N>(r);
+    if (h0 && r0 && !p_inf && !skip) {  // same point: rare, data dependent — take the doubling path
+        pt_double<C>(P);
+        return;
+    }
+    uint32_t hh[N], hhh[N], v[N], x3[N], y3[N], z3[N];
+    C::fsqr(hh, h);
+    C::fmul(hhh, h, hh);
+    C::fmul(v, u1, hh);
+    C::fsqr(x3, r);
+    C::fsub(x3, x3, hhh);
+    C::fsub(x3, x3, v);
+    C::fsub(x3, x3, v);
+    C::fsub(t, v, x3);
+    C::fmul(y3, r, t);
+    C::fmul(t, s1, hhh);
+    C::fsub(y3, y3, t);
+    C::fmul(z3, P.Z, h);
+    if (!AFFINE) C::fmul(z3, z3, z2);
+    // select: skip -> P ; P inf -> addend ; else sum
+    uint32_t one[N];
+    C::get_one(one);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        uint32_t ax = x2[i], ay = y2[i], az = AFFINE ? one[i] : z2[i];
+        uint32_t nx = p_inf ? ax : x3[i], ny = p_inf ? ay : y3[i], nz = p_inf ? az : z3[i];
+        P.X[i] = skip ? P.X[i] : nx;
+        P.Y[i] = skip ? P.Y[i] : ny;
+        P.Z[i] = skip ? P.Z[i] : nz;
+    }
+}
+
+// r = a^(p-2) (field inverse, Montgomery in/out); a != 0.  Setup paths only.
+template <class C>
+__device__ __noinline__ void f_inv(uint32_t (&r)[C::N], const uint32_t (&a)[C::N]) {
+    constexpr int N = C::N;
+    uint32_t acc[N];
+    C::get_one(acc);
+    for (int i = 32 * N - 1; i >= 0; i--) {
+        C::fsqr(acc, acc);
+        if ((C::p_minus_2_limb(i >> 5) >> (i & 31)) & 1u) C::fmul(acc, acc, a);
+    }
+    mp_copy<N>(r, acc);
+}
+// r = a^(n-2) mod n (Montgomery form in/out, R = 2^(32N))
+template <class C>
+__device__ __noinline__ void n_inv(uint32_t (&r)[C::N], const uint32_t (&a)[C::N]) {
+    constexpr int N = C::N;
+    uint32_t acc[N];
+    C::get_one_n(acc);
+    for (int i = 32 * N - 1; i >= 0; i--) {
+        C::nmul(acc, acc, acc);
+        if ((C::n_minus_2_limb(i >> 5) >> (i & 31)) & 1u) C::nmul(acc, acc, a);
+    }
+    mp_copy<N>(r, acc);
+}
+
+// big-endian byte string (C::BYTES, 4-byte aligned) -> little-endian limbs
+template <int N>
+SBV_DEV void load_be(uint32_t (&r)[N], const uint8_t *src) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(src);
+#pragma unroll
+    for (int i = 0; i < N; i++) r[N - 1 - i] = __byte_perm(__ldg(w + i), 0, 0x0123);
+}
+
+}  // namespace sbv

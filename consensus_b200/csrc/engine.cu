@@ -1,0 +1,376 @@
+// engine.cu — host side of libsbv.so: the C ABI of include/sbv.h on top of the sm_100a kernels.
+//
+// One engine owns 1..8 devices of one box.  Every batch is sharded into contiguous ranges, one per
+// device; each device has its own stream, workspace and pinned staging buffer.  No CPU fallback.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sbv.h"
+#include "kernels.cuh"
+#include "sha256.cuh"
+#include "quorum.cuh"
+
+using namespace sbv;
+
+namespace {
+
+struct Dev {
+    int ordinal = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t *gtab[2] = {nullptr, nullptr};
+    // per-batch workspace (device)
+    size_t cap = 0;
+    uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr, *d_qy = nullptr, *d_dig = nullptr, *d_ok = nullptr;
+    uint8_t *d_gidx = nullptr, *d_flags = nullptr;
+    int8_t *d_digits = nullptr;
+    // message workspace
+    size_t msg_cap = 0, off_cap = 0;
+    uint8_t *d_msgs = nullptr;
+    uint64_t *d_off = nullptr;
+    // pinned staging
+    uint8_t *h_pin = nullptr;
+    size_t h_pin_cap = 0;
+    // generic scratch (quorum, bitmask)
+    uint8_t *d_scratch = nullptr;
+    size_t scratch_cap = 0;
+};
+
+}  // namespace
+
+struct sbv_engine {
+    std::vector<Dev> devs;
+    std::mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    int p256_w = 4, p256_block = 128, p384_w = 3, p384_block = 128;
+    // NCCL (multi-device only; loaded lazily with dlopen so single-device users never touch it)
+    void *nccl_lib = nullptr;
+    std::vector<void *> nccl_comms;
+    // key registry
+    uint64_t verification_seq = 0;
+    std::vector<uint64_t> key_ids;
+    std::vector<uint8_t> key_curve;
+    std::vector<uint8_t> key_xy;
+};
+
+namespace {
+
+int fail(sbv_engine *e, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf;
+    return code;
+}
+
+#define CU(e, call)                                                                               \
+    do {                                                                                          \
+        cudaError_t _st = (call);                                                                 \
+        if (_st != cudaSuccess)                                                                   \
+            return fail(e, SBV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), \
+                        __FILE__, __LINE__);                                                      \
+    } while (0)
+
+int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+size_t fbytes(uint8_t curve) { return curve == SBV_P256 ? 32 : 48; }
+
+int ensure_workspace(sbv_engine *e, Dev &d, size_t n) {
+    if (n <= d.cap) return 0;
+    size_t cap = n + n / 8 + 1024;
+    CU(e, cudaSetDevice(d.ordinal));
+    uint8_t **ptrs[] = {&d.d_r, &d.d_s, &d.d_qx, &d.d_qy, &d.d_dig, &d.d_ok, &d.d_gidx, &d.d_flags};
+    for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+    if (d.d_digits) cudaFree(d.d_digits);
+    CU(e, cudaMalloc(&d.d_r, cap * 48));
+    CU(e, cudaMalloc(&d.d_s, cap * 48));
+    CU(e, cudaMalloc(&d.d_qx, cap * 48));
+    CU(e, cudaMalloc(&d.d_qy, cap * 48));
+    CU(e, cudaMalloc(&d.d_dig, cap * 64));
+    CU(e, cudaMalloc(&d.d_ok, cap));
+    CU(e, cudaMalloc(&d.d_gidx, cap * 48));
+    CU(e, cudaMalloc(&d.d_flags, cap));
+    CU(e, cudaMalloc(&d.d_digits, cap * 132));
+    d.cap = cap;
+    return 0;
+}
+
+int ensure_pinned(sbv_engine *e, Dev &d, size_t bytes) {
+    if (bytes <= d.h_pin_cap) return 0;
+    CU(e, cudaSetDevice(d.ordinal));
+    if (d.h_pin) cudaFreeHost(d.h_pin);
+    d.h_pin = nullptr;
+    size_t cap = bytes + bytes / 4 + 4096;
+    CU(e, cudaHostAlloc(&d.h_pin, cap, cudaHostAllocPortable));
+    d.h_pin_cap = cap;
+    return 0;
+}
+
+int ensure_scratch(sbv_engine *e, Dev &d, size_t bytes) {
+    if (bytes <= d.scratch_cap) return 0;
+    CU(e, cudaSetDevice(d.ordinal));
+    if (d.d_scratch) cudaFree(d.d_scratch);
+    d.d_scratch = nullptr;
+    size_t cap = bytes + bytes / 4 + 4096;
+    CU(e, cudaMalloc(&d.d_scratch, cap));
+    d.scratch_cap = cap;
+    return 0;
+}
+
+int ensure_msgs(sbv_engine *e, Dev &d, size_t bytes, size_t n_off) {
+    CU(e, cudaSetDevice(d.ordinal));
+    if (bytes > d.msg_cap) {
+        if (d.d_msgs) cudaFree(d.d_msgs);
+        d.d_msgs = nullptr;
+        size_t cap = bytes + bytes / 8 + 4096;
+        CU(e, cudaMalloc(&d.d_msgs, cap));
+        d.msg_cap = cap;
+    }
+    if (n_off > d.off_cap) {
+        if (d.d_off) cudaFree(d.d_off);
+        d.d_off = nullptr;
+        size_t cap = n_off + n_off / 8 + 1024;
+        CU(e, cudaMalloc(&d.d_off, cap * sizeof(uint64_t)));
+        d.off_cap = cap;
+    }
+    return 0;
+}
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// H2D of a caller buffer: direct when pinned, else through the device's pinned staging area at
+// offset `stage_off` (caller guarantees the staging area is large enough and not reused until the
+// stream has drained).
+int h2d(sbv_engine *e, Dev &d, void *dst, const void *src, size_t bytes, size_t &stage_off, cudaStream_t st) {
+    if (bytes == 0) return 0;
+    if (is_pinned(src)) {
+        CU(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    } else {
+        memcpy(d.h_pin + stage_off, src, bytes);
+        CU(e, cudaMemcpyAsync(dst, d.h_pin + stage_off, bytes, cudaMemcpyHostToDevice, st));
+        stage_off += (bytes + 255) & ~(size_t)255;
+    }
+    return 0;
+}
+
+template <class C, int W, int BLOCK>
+int launch_verify_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
+                    const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st,
+                    int curve_idx) {
+    constexpr int S = 8;
+    constexpr int TE = Windows<32 * C::N, W>::ENTRIES;
+    const uint32_t nn = (uint32_t)n;
+    uint32_t pthreads = (nn + S - 1) / S;
+    uint32_t pblocks = (pthreads + 127) / 128;
+    k_prep<C, W, S><<<pblocks, 128, 0, st>>>(nn, d_r, d_s, d_dig, dlen, d.d_gidx, d.d_digits, d.d_flags);
+    size_t smem = (size_t)TE * 3 * C::N * 4 * BLOCK;
+    static bool attr_set[8] = {false};
+    (void)attr_set;
+    CU(e, cudaFuncSetAttribute(k_verify<C, W, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    uint32_t vblocks = (nn + BLOCK - 1) / BLOCK;
+    k_verify<C, W, BLOCK><<<vblocks, BLOCK, smem, st>>>(nn, d_qx, d_qy, d_r, d.d_gidx, d.d_digits, d.d_flags,
+                                                        reinterpret_cast<const uint4 *>(d.gtab[curve_idx]), d_ok);
+    e->launches += 2;
+    CU(e, cudaGetLastError());
+    return 0;
+}
+
+// inputs on device d; enqueues on st; no sync
+int launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_r, const uint8_t *d_s,
+                  const uint8_t *d_qx, const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok,
+                  cudaStream_t st) {
+    if (n == 0) return 0;
+    if (curve == SBV_P256) {
+        if (e->p256_w == 3) return launch_verify_t<P256, 3, 128>(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st, 0);
+        if (e->p256_block == 64) return launch_verify_t<P256, 4, 64>(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st, 0);
+        return launch_verify_t<P256, 4, 128>(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st, 0);
+    }
+    return launch_verify_t<P384, 3, 128>(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st, 1);
+}
+
+__global__ void k_mad_probe(uint32_t *out, uint32_t iters) {
+    uint32_t a = threadIdx.x * 2654435761u + 12345u, b = blockIdx.x * 40503u + 777u;
+    uint64_t acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = a + i;
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = (uint64_t)a * (uint32_t)(b + i) + acc[i];  // IMAD.WIDE.U32
+        a ^= (uint32_t)acc[3];
+    }
+    uint64_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += acc[i];
+    if (s == 0x1234567) out[0] = (uint32_t)s;
+}
+
+struct Shard { size_t lo, n; };
+Shard shard_of(size_t n, int g, int G) {
+    size_t lo = n * g / G, hi = n * (g + 1) / G;
+    return {lo, hi - lo};
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
+    if (!out || n_devices < 1 || n_devices > 8) return SBV_ERR_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count < n_devices) return SBV_ERR_CUDA;
+    sbv_engine *e = new sbv_engine();
+    e->p256_w = env_int("SBV_P256_W", 4);
+    e->p256_block = env_int("SBV_P256_BLOCK", 128);
+    e->devs.resize(n_devices);
+    for (int g = 0; g < n_devices; g++) {
+        Dev &d = e->devs[g];
+        d.ordinal = device_ordinals ? device_ordinals[g] : g;
+        cudaError_t st = cudaSetDevice(d.ordinal);
+        if (st == cudaSuccess) st = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        if (st == cudaSuccess) st = cudaMalloc(&d.gtab[0], (size_t)32 * 256 * 16 * 4);
+        if (st == cudaSuccess) st = cudaMalloc(&d.gtab[1], (size_t)48 * 256 * 24 * 4);
+        if (st == cudaSuccess) {
+            k_gtable_init<P256><<<32 * 256 / 128, 128, 0, d.stream>>>(d.gtab[0]);
+            k_gtable_init<P384><<<48 * 256 / 128, 128, 0, d.stream>>>(d.gtab[1]);
+            e->launches += 2;
+            st = cudaStreamSynchronize(d.stream);
+        }
+        if (st != cudaSuccess) {
+            fprintf(stderr, "sbv_create: device %d: %s\n", d.ordinal, cudaGetErrorString(st));
+            sbv_destroy(e);
+            return SBV_ERR_CUDA;
+        }
+    }
+    *out = e;
+    return SBV_OK;
+}
+
+void sbv_destroy(sbv_engine *e) {
+    if (!e) return;
+    for (Dev &d : e->devs) {
+        cudaSetDevice(d.ordinal);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        void *ptrs[] = {d.gtab[0], d.gtab[1], d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, d.d_ok, d.d_gidx, d.d_flags,
+                        d.d_digits, d.d_msgs, d.d_off, d.d_scratch};
+        for (void *p : ptrs) if (p) cudaFree(p);
+        if (d.h_pin) cudaFreeHost(d.h_pin);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete e;
+}
+
+const char *sbv_last_error(const sbv_engine *e) { return e ? e->err.c_str() : "null engine"; }
+int sbv_device_count(const sbv_engine *e) { return e ? (int)e->devs.size() : 0; }
+uint64_t sbv_kernel_launches(const sbv_engine *e) { return e ? e->launches : 0; }
+
+void sbv_compute_quorum(uint64_t n, uint32_t *q, uint32_t *f) {
+    // f = (n-1)/3 ; q = ceil((n+f+1)/2) — util.go:183-187, exact in integers
+    uint64_t ff = n ? (n - 1) / 3 : 0;
+    if (f) *f = (uint32_t)ff;
+    if (q) *q = (uint32_t)((n + ff + 2) / 2);
+}
+
+int sbv_verify_batch_device(sbv_engine *e, int device_index, uint8_t curve, size_t n, const uint8_t *d_r,
+                            const uint8_t *d_s, const uint8_t *d_qx, const uint8_t *d_qy, const uint8_t *d_digest,
+                            uint8_t digest_len, uint8_t *d_ok, void *cuda_stream) {
+    if (!e || curve > SBV_P384 || device_index < 0 || device_index >= (int)e->devs.size() || digest_len == 0)
+        return fail(e, SBV_ERR_ARG, "sbv_verify_batch_device: bad argument");
+    if (n == 0) return SBV_OK;
+    if (n > 0x7fffffffu || (digest_len & 3)) return fail(e, SBV_ERR_ARG, "n too large or digest_len not a multiple of 4");
+    std::lock_guard<std::mutex> lk(e->mu);
+    Dev &d = e->devs[device_index];
+    CU(e, cudaSetDevice(d.ordinal));
+    int rc = ensure_workspace(e, d, n);
+    if (rc) return rc;
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : d.stream;
+    return launch_verify(e, d, curve, n, d_r, d_s, d_qx, d_qy, d_digest, digest_len, d_ok, st);
+}
+
+int sbv_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *r, const uint8_t *s, const uint8_t *qx,
+                     const uint8_t *qy, const uint8_t *digest, uint8_t digest_len, uint8_t *ok) {
+    if (!e || curve > SBV_P384 || digest_len == 0 || (digest_len & 3) || digest_len > 64)
+        return fail(e, SBV_ERR_ARG, "sbv_verify_batch: bad argument");
+    if (n == 0) return SBV_OK;
+    if (!r || !s || !qx || !qy || !digest || !ok) return fail(e, SBV_ERR_ARG, "null buffer");
+    std::lock_guard<std::mutex> lk(e->mu);
+    const size_t L = fbytes(curve);
+    const int G = (int)e->devs.size();
+    for (int g = 0; g < G; g++) {
+        Dev &d = e->devs[g];
+        Shard sh = shard_of(n, g, G);
+        if (sh.n == 0) continue;
+        CU(e, cudaSetDevice(d.ordinal));
+        int rc = ensure_workspace(e, d, sh.n);
+        if (rc) return rc;
+        rc = ensure_pinned(e, d, sh.n * (4 * L + digest_len + 1) + 8 * 256);
+        if (rc) return rc;
+        size_t so = 0;
+        if ((rc = h2d(e, d, d.d_r, r + sh.lo * L, sh.n * L, so, d.stream))) return rc;
+        if ((rc = h2d(e, d, d.d_s, s + sh.lo * L, sh.n * L, so, d.stream))) return rc;
+        if ((rc = h2d(e, d, d.d_qx, qx + sh.lo * L, sh.n * L, so, d.stream))) return rc;
+        if ((rc = h2d(e, d, d.d_qy, qy + sh.lo * L, sh.n * L, so, d.stream))) return rc;
+        if ((rc = h2d(e, d, d.d_dig, digest + sh.lo * digest_len, sh.n * digest_len, so, d.stream))) return rc;
+        rc = launch_verify(e, d, curve, sh.n, d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, digest_len, d.d_ok, d.stream);
+        if (rc) return rc;
+        CU(e, cudaMemcpyAsync(ok + sh.lo, d.d_ok, sh.n, cudaMemcpyDeviceToHost, d.stream));
+    }
+    for (int g = 0; g < G; g++) {
+        CU(e, cudaSetDevice(e->devs[g].ordinal));
+        CU(e, cudaStreamSynchronize(e->devs[g].stream));
+    }
+    return SBV_OK;
+}
+
+double sbv_probe_mad_rate(sbv_engine *e) {
+    if (!e) return 0.0;
+    std::lock_guard<std::mutex> lk(e->mu);
+    Dev &d = e->devs[0];
+    if (cudaSetDevice(d.ordinal) != cudaSuccess) return 0.0;
+    if (ensure_scratch(e, d, 4096)) return 0.0;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, d.ordinal);
+    const uint32_t iters = 4096;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    k_mad_probe<<<blocks, threads, 0, d.stream>>>((uint32_t *)d.d_scratch, 64);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(a, d.stream);
+        k_mad_probe<<<blocks, threads, 0, d.stream>>>((uint32_t *)d.d_scratch, iters);
+        cudaEventRecord(b, d.stream);
+        if (cudaStreamSynchronize(d.stream) != cudaSuccess) return 0.0;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (ms < best) best = ms;
+    }
+    e->launches += 6;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    double macs = (double)blocks * threads * (double)iters * 8.0;
+    return macs / (best * 1e-3);
+}
+
+}  // extern "C"
+
+#include "engine_more.inc"

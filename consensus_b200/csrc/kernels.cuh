@@ -1,0 +1,279 @@
+// kernels.cuh — sm_100a kernels of the sbv hot path (ECDSA verify over NIST prime curves).
+//
+//   k_gtable_init  one-time: affine fixed-base comb table  T[i][b] = b * 2^(8i) * G  (Montgomery form)
+//   k_prep         per batch: range checks, batched inversion of s mod n (Montgomery's trick, S items
+//                  per thread), u1 = e/s, u2 = r/s, comb bytes of u1 and Booth digits of u2 written
+//                  window-major so the verify kernel reads them coalesced
+//   k_verify       per batch, ONE SIGNATURE PER THREAD: on-curve check, per-thread window table of Q in
+//                  shared memory (bank = lane, so data-dependent indices never conflict), interleaved
+//                  double-and-add for u2*Q, comb adds for u1*G from the L2-resident table, final
+//                  X == r*Z^2 comparison (no inversion)
+//
+// Reference boundary: api.Verifier.VerifyConsenterSig / VerifySignature / VerifyRequest
+// (/root/reference/pkg/api/dependencies.go:54-71) — the arithmetic itself is Go crypto/ecdsa
+// semantics (see include/sbv.h).
+#pragma once
+#include "curve.cuh"
+
+namespace sbv {
+
+template <int BITS, int W>
+struct Windows {
+    static constexpr int COUNT = (BITS + 1 + W - 1) / W;  // Booth windows covering BITS+1 bits
+    static constexpr int ENTRIES = 1 << (W - 1);          // table holds 1..2^(W-1) times Q
+};
+
+// ------------------------------------------------------------------------------------------------
+template <class C>
+__global__ void k_gtable_init(uint32_t *__restrict__ gtab) {
+    constexpr int N = C::N;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= C::BYTES * 256) return;
+    const int win = t >> 8, b = t & 255;
+    uint32_t *out = gtab + (size_t)t * 2 * N;
+    if (b == 0) {
+        for (int i = 0; i < 2 * N; i++) out[i] = 0;
+        return;
+    }
+    Jac<C> base;
+    C::get_gx(base.X); C::get_gy(base.Y); C::get_one(base.Z);
+    for (int i = 0; i < 8 * win; i++) pt_double<C>(base);
+    Jac<C> acc;
+    C::get_one(acc.X); C::get_one(acc.Y);
+#pragma unroll
+    for (int i = 0; i < N; i++) acc.Z[i] = 0;
+    for (int bit = 7; bit >= 0; bit--) {
+        pt_double<C>(acc);
+        pt_add<C, false>(acc, base.X, base.Y, base.Z, false, !((b >> bit) & 1));
+    }
+    uint32_t zi[N], zi2[N], zi3[N], x[N], y[N];
+    f_inv<C>(zi, acc.Z);
+    C::fsqr(zi2, zi);
+    C::fmul(zi3, zi2, zi);
+    C::fmul(x, acc.X, zi2);
+    C::fmul(y, acc.Y, zi3);
+    for (int i = 0; i < N; i++) { out[i] = x[i]; out[N + i] = y[i]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// digest -> e: leftmost min(dlen, BYTES) bytes as a big-endian integer (crypto/ecdsa hashToNat).
+template <class C>
+SBV_DEV void load_digest(uint32_t (&e)[C::N], const uint8_t *d, uint32_t dlen) {
+    constexpr int N = C::N;
+    if (dlen == (uint32_t)C::BYTES) { load_be<N>(e, d); return; }
+    const int L = dlen < (uint32_t)C::BYTES ? (int)dlen : C::BYTES;
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int pos = L - 1 - (4 * j + k);
+            uint32_t byte = pos >= 0 ? (uint32_t)d[pos] : 0u;
+            v |= byte << (8 * k);
+        }
+        e[j] = v;
+    }
+}
+
+template <class C, int W, int S>
+__global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restrict__ r_be, const uint8_t *__restrict__ s_be,
+                                              const uint8_t *__restrict__ dig_be, uint32_t dlen,
+                                              uint8_t *__restrict__ gidx, int8_t *__restrict__ digits,
+                                              uint8_t *__restrict__ flags) {
+    constexpr int N = C::N;
+    constexpr int NWIN = Windows<32 * N, W>::COUNT;
+    const uint32_t T = gridDim.x * blockDim.x;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t sm[S][N];    // Montgomery form of s (or 1 when out of range)
+    uint32_t pref[S][N];  // running products
+    uint32_t nmod[N], rr[N];
+    C::get_n(nmod);
+    C::get_rr_n(rr);
+    uint32_t run[N];
+    C::get_one_n(run);
+    int cnt = 0;
+    for (int k = 0; k < S; k++) {
+        uint32_t idx = t + (uint32_t)k * T;
+        if (idx >= n) break;
+        uint32_t s[N], r[N];
+        load_be<N>(s, s_be + (size_t)idx * C::BYTES);
+        load_be<N>(r, r_be + (size_t)idx * C::BYTES);
+        bool ok = !mp_is_zero<N>(s) && mp_lt<N>(s, nmod) && !mp_is_zero<N>(r) && mp_lt<N>(r, nmod);
+        flags[idx] = ok ? 1 : 0;
+        uint32_t one[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) one[i] = (i == 0);
+        uint32_t sv[N];
+        mp_select<N>(sv, ok, s, one);
+        uint32_t m[N];
+        C::nmul(m, sv, rr);
+        C::nmul(run, run, m);
+#pragma unroll
+        for (int i = 0; i < N; i++) { sm[k][i] = m[i]; pref[k][i] = run[i]; }
+        cnt++;
+    }
+    if (cnt == 0) return;
+    uint32_t inv[N];
+    n_inv<C>(inv, run);
+    for (int k = cnt - 1; k >= 0; k--) {
+        uint32_t idx = t + (uint32_t)k * T;
+        uint32_t w[N], m[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) m[i] = sm[k][i];
+        if (k > 0) {
+            uint32_t pv[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) pv[i] = pref[k - 1][i];
+            C::nmul(w, inv, pv);
+            C::nmul(inv, inv, m);
+        } else {
+            mp_copy<N>(w, inv);
+        }
+        // w = s^-1 in Montgomery form; u = x * w (plain) for x < 2^(32N)
+        uint32_t e[N], r[N], u1[N], u2[N + 1];
+        load_digest<C>(e, dig_be + (size_t)idx * dlen, dlen);
+        load_be<N>(r, r_be + (size_t)idx * C::BYTES);
+        C::nmul(u1, e, w);
+        {
+            uint32_t tmp[N];
+            C::nmul(tmp, r, w);
+#pragma unroll
+            for (int i = 0; i < N; i++) u2[i] = tmp[i];
+            u2[N] = 0;
+        }
+        // comb bytes of u1 (window i = byte i, little-endian)
+#pragma unroll
+        for (int i = 0; i < C::BYTES; i++) gidx[(size_t)i * n + idx] = (uint8_t)(u1[i >> 2] >> (8 * (i & 3)));
+        // Booth digits of u2: window i looks at bits [W*i-1, W*i+W-1]
+        for (int i = 0; i < NWIN; i++) {
+            int pos = W * i - 1;
+            uint32_t b;
+            if (pos < 0) {
+                b = (u2[0] << 1) & ((2u << W) - 1);
+            } else {
+                int wd = pos >> 5, sh = pos & 31;
+                uint32_t lo = wd <= N ? u2[wd] : 0u, hi = wd + 1 <= N ? u2[wd + 1] : 0u;
+                uint64_t v = ((uint64_t)hi << 32) | lo;
+                b = (uint32_t)(v >> sh) & ((2u << W) - 1);
+            }
+            uint32_t sign = b >> W;
+            uint32_t d = sign ? (((2u << W) - 1) - b) : b;
+            d = (d + 1) >> 1;
+            digits[(size_t)i * n + idx] = (int8_t)(sign ? -(int)d : (int)d);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+template <class C, int W, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_verify(uint32_t n, const uint8_t *__restrict__ qx_be, const uint8_t *__restrict__ qy_be,
+                                                  const uint8_t *__restrict__ r_be, const uint8_t *__restrict__ gidx,
+                                                  const int8_t *__restrict__ digits, const uint8_t *__restrict__ flags,
+                                                  const uint4 *__restrict__ gtab, uint8_t *__restrict__ ok_out) {
+    constexpr int N = C::N;
+    constexpr int NWIN = Windows<32 * N, W>::COUNT;
+    constexpr int TE = Windows<32 * N, W>::ENTRIES;
+    extern __shared__ uint32_t tab[];  // [(entry*3 + coord)*N + limb][BLOCK]
+    const uint32_t tid = threadIdx.x;
+    const uint32_t idx = blockIdx.x * BLOCK + tid;
+    if (idx >= n) return;  // the table is thread-private: no block-wide barrier anywhere
+#define TAB(e, c, w) tab[(((e) * 3 + (c)) * N + (w)) * BLOCK + tid]
+
+    uint32_t pmod[N], one[N];
+    C::get_p(pmod);
+    C::get_one(one);
+    bool good = flags[idx] != 0;
+    {
+        uint32_t x[N], y[N], rr[N];
+        load_be<N>(x, qx_be + (size_t)idx * C::BYTES);
+        load_be<N>(y, qy_be + (size_t)idx * C::BYTES);
+        good = good && mp_lt<N>(x, pmod) && mp_lt<N>(y, pmod);
+        C::get_rr_p(rr);
+        Jac<C> P;
+        C::fmul(P.X, x, rr);
+        C::fmul(P.Y, y, rr);
+        mp_copy<N>(P.Z, one);
+        // y^2 == x^3 - 3x + b
+        uint32_t lhs[N], rhs[N], t[N], b[N];
+        C::fsqr(lhs, P.Y);
+        C::fsqr(t, P.X);
+        C::fmul(rhs, t, P.X);
+        C::fsub(rhs, rhs, P.X);
+        C::fsub(rhs, rhs, P.X);
+        C::fsub(rhs, rhs, P.X);
+        C::get_b(b);
+        C::fadd(rhs, rhs, b);
+        good = good && mp_eq<N>(lhs, rhs);
+        // table: entry k-1 holds k*Q (Jacobian)
+        uint32_t qxm[N], qym[N];
+        mp_copy<N>(qxm, P.X);
+        mp_copy<N>(qym, P.Y);
+#pragma unroll 1
+        for (int k = 0; k < TE; k++) {
+            if (k == 1) pt_double<C>(P);
+            else if (k > 1) pt_add<C, true>(P, qxm, qym, one, false, false);
+#pragma unroll
+            for (int i = 0; i < N; i++) { TAB(k, 0, i) = P.X[i]; TAB(k, 1, i) = P.Y[i]; TAB(k, 2, i) = P.Z[i]; }
+        }
+    }
+    Jac<C> acc;
+    mp_copy<N>(acc.X, one);
+    mp_copy<N>(acc.Y, one);
+#pragma unroll
+    for (int i = 0; i < N; i++) acc.Z[i] = 0;
+
+#pragma unroll 1
+    for (int win = NWIN - 1; win >= 0; win--) {
+        if (win != NWIN - 1) {
+#pragma unroll 1
+            for (int k = 0; k < W; k++) pt_double<C>(acc);
+        }
+        {
+            int d = digits[(size_t)win * n + idx];
+            bool neg = d < 0, skip = d == 0;
+            int e = (neg ? -d : d) - 1;
+            e = skip ? 0 : e;
+            uint32_t x2[N], y2[N], z2[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) { x2[i] = TAB(e, 0, i); y2[i] = TAB(e, 1, i); z2[i] = TAB(e, 2, i); }
+            pt_add<C, false>(acc, x2, y2, z2, neg, skip);
+        }
+        if (win < C::BYTES) {
+            uint32_t b = gidx[(size_t)win * n + idx];
+            const uint4 *src = gtab + ((size_t)win * 256 + b) * (2 * N / 4);
+            uint32_t x2[N], y2[N];
+#pragma unroll
+            for (int i = 0; i < N / 4; i++) {
+                uint4 v = __ldg(src + i);
+                x2[4 * i] = v.x; x2[4 * i + 1] = v.y; x2[4 * i + 2] = v.z; x2[4 * i + 3] = v.w;
+                uint4 u = __ldg(src + N / 4 + i);
+                y2[4 * i] = u.x; y2[4 * i + 1] = u.y; y2[4 * i + 2] = u.z; y2[4 * i + 3] = u.w;
+            }
+            pt_add<C, true>(acc, x2, y2, one, false, b == 0);
+        }
+    }
+#undef TAB
+    // accept iff R != inf and R.x mod n == r  <=>  X == r*Z^2 or (r + n < p and X == (r+n)*Z^2)
+    bool match = false;
+    if (!mp_is_zero<N>(acc.Z)) {
+        uint32_t zz[N], r[N], rr[N], rm[N], lhs[N], pmn[N];
+        C::fsqr(zz, acc.Z);
+        load_be<N>(r, r_be + (size_t)idx * C::BYTES);
+        C::get_rr_p(rr);
+        C::fmul(rm, r, rr);
+        C::fmul(lhs, rm, zz);
+        match = mp_eq<N>(lhs, acc.X);
+        C::get_p_minus_n(pmn);
+        if (!match && mp_lt<N>(r, pmn)) {
+            uint32_t r2[N], nmod[N];
+            C::get_n(nmod);
+            mp_add<N>(r2, r, nmod);
+            C::fmul(rm, r2, rr);
+            C::fmul(lhs, rm, zz);
+            match = mp_eq<N>(lhs, acc.X);
+        }
+    }
+    ok_out[idx] = (good && match) ? 1 : 0;
+}
+
+}  // namespace sbv

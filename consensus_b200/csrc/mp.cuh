@@ -1,0 +1,173 @@
+// mp.cuh — register-resident multiprecision primitives for sm_100a (32-bit limbs, little-endian).
+//
+// The multiply uses the even/odd column split: every a[i]*b[j] with i+j even is a 64-bit value at
+// an even limb offset, so a row of them is one carry chain of IMAD.WIDE.U32.X instructions
+// (ptxas fuses each mad.lo.cc/madc.hi.cc pair into a single wide MAD with a carry predicate);
+// the odd columns go to a second accumulator that is added back shifted by one limb.
+// N*N wide MADs + 2N carry words + one 2N-limb add per product.
+#pragma once
+#include <stdint.h>
+
+namespace sbv {
+
+#define SBV_DEV __device__ __forceinline__
+
+SBV_DEV uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+SBV_DEV uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+SBV_DEV uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+SBV_DEV uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+SBV_DEV uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+SBV_DEV uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+
+// (hi:lo) += a*b, carry-out to CC                 [first link of a chain]
+SBV_DEV void mad_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// (hi:lo) += a*b + CC, carry-out to CC            [inner link]
+SBV_DEV void madc_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+
+// r[0..2N) = a[0..N) * b[0..N)
+template <int N>
+SBV_DEV void mp_mul(uint32_t (&r)[2 * N], const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+    static_assert(N % 2 == 0, "even limb count");
+    uint32_t E[2 * N], O[2 * N];  // O[k] has weight 2^(32(k+1))
+#pragma unroll
+    for (int i = 0; i < 2 * N; i++) { E[i] = 0; O[i] = 0; }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        if ((j & 1) == 0) {
+            // i even -> E at limb i+j ; i odd -> O at index i+j-1
+            mad_wide_cc(E[j], E[j + 1], a[0], b[j]);
+#pragma unroll
+            for (int i = 2; i < N; i += 2) madc_wide_cc(E[i + j], E[i + j + 1], a[i], b[j]);
+            E[j + N] = addc(E[j + N], 0);
+            mad_wide_cc(O[j], O[j + 1], a[1], b[j]);
+#pragma unroll
+            for (int i = 3; i < N; i += 2) madc_wide_cc(O[i + j - 1], O[i + j], a[i], b[j]);
+            O[j + N] = addc(O[j + N], 0);
+        } else {
+            // i odd -> E at limb i+j ; i even -> O at index i+j-1
+            mad_wide_cc(E[j + 1], E[j + 2], a[1], b[j]);
+#pragma unroll
+            for (int i = 3; i < N; i += 2) madc_wide_cc(E[i + j], E[i + j + 1], a[i], b[j]);
+            if (j + N + 1 < 2 * N) E[j + N + 1] = addc(E[j + N + 1], 0);
+            mad_wide_cc(O[j - 1], O[j], a[0], b[j]);
+#pragma unroll
+            for (int i = 2; i < N; i += 2) madc_wide_cc(O[i + j - 1], O[i + j], a[i], b[j]);
+            O[j + N - 1] = addc(O[j + N - 1], 0);
+        }
+    }
+    r[0] = E[0];
+    r[1] = add_cc(E[1], O[0]);
+#pragma unroll
+    for (int i = 2; i < 2 * N - 1; i++) r[i] = addc_cc(E[i], O[i - 1]);
+    r[2 * N - 1] = addc(E[2 * N - 1], O[2 * N - 2]);
+}
+
+// r = a + b, returns carry-out
+template <int N>
+SBV_DEV uint32_t mp_add(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+    r[0] = add_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r[i] = addc_cc(a[i], b[i]);
+    return addc(0, 0);
+}
+// r = a - b, returns borrow (1 if a < b)
+template <int N>
+SBV_DEV uint32_t mp_sub(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+    r[0] = sub_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) r[i] = subc_cc(a[i], b[i]);
+    return subc(0, 0) & 1u;  // subc(0,0) = -borrow
+}
+template <int N>
+SBV_DEV bool mp_is_zero(const uint32_t (&a)[N]) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= a[i];
+    return o == 0;
+}
+template <int N>
+SBV_DEV bool mp_eq(const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) o |= a[i] ^ b[i];
+    return o == 0;
+}
+// a < b ?
+template <int N>
+SBV_DEV bool mp_lt(const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+    uint32_t t[N];
+    return mp_sub<N>(t, a, b) != 0;
+}
+template <int N>
+SBV_DEV void mp_copy(uint32_t (&r)[N], const uint32_t (&a)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = a[i];
+}
+// r = c ? a : b
+template <int N>
+SBV_DEV void mp_select(uint32_t (&r)[N], bool c, const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; i++) r[i] = c ? a[i] : b[i];
+}
+
+// ---- modular helpers for a modulus m (canonical residues in [0, m)) ----
+template <int N>
+SBV_DEV void mod_add(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&b)[N], const uint32_t (&m)[N]) {
+    uint32_t s[N], t[N];
+    uint32_t c = mp_add<N>(s, a, b);
+    uint32_t bw = mp_sub<N>(t, s, m);
+    bool use_t = (c != 0) || (bw == 0);
+    mp_select<N>(r, use_t, t, s);
+}
+template <int N>
+SBV_DEV void mod_sub(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&b)[N], const uint32_t (&m)[N]) {
+    uint32_t d[N];
+    uint32_t bw = mp_sub<N>(d, a, b);
+    uint32_t mask = 0u - bw;
+    r[0] = add_cc(d[0], m[0] & mask);
+#pragma unroll
+    for (int i = 1; i < N - 1; i++) r[i] = addc_cc(d[i], m[i] & mask);
+    r[N - 1] = addc(d[N - 1], m[N - 1] & mask);
+}
+
+// Generic word-serial Montgomery product r = a*b*2^(-32N) mod m, minv = -m^-1 mod 2^32.
+// a, b < m.  Used for arithmetic mod the group order n and for the P-384 field.
+template <int N>
+SBV_DEV void mont_mul_generic(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&b)[N],
+                              const uint32_t (&m)[N], uint32_t minv) {
+    uint32_t T[2 * N];
+    mp_mul<N>(T, a, b);
+    uint32_t top = 0;  // carry limb above T[2N-1]
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        uint32_t q = T[i] * minv;
+        // T[i..i+N] += q*m  (even/odd would need two accumulators; a 64-bit carry walk is fine here)
+        uint64_t c = 0;
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            uint64_t v = (uint64_t)q * m[j] + T[i + j] + c;
+            T[i + j] = (uint32_t)v;
+            c = v >> 32;
+        }
+        // propagate c upward
+#pragma unroll
+        for (int j = i + N; j < 2 * N; j++) {
+            uint64_t v = (uint64_t)T[j] + c;
+            T[j] = (uint32_t)v;
+            c = v >> 32;
+        }
+        top += (uint32_t)c;
+    }
+    uint32_t hi[N], t[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) hi[i] = T[N + i];
+    uint32_t bw = mp_sub<N>(t, hi, m);
+    bool use_t = (top != 0) || (bw == 0);
+    mp_select<N>(r, use_t, t, hi);
+}
+
+}  // namespace sbv

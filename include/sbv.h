@@ -1,0 +1,121 @@
+/*
+ * sbv.h — C ABI of the B200-native batched signature-verification engine.
+ *
+ * This is the drop-in boundary behind SmartBFT's application-implemented verifier plug-in:
+ *   api.Verifier            /root/reference/pkg/api/dependencies.go:54-71
+ *     VerifyConsenterSig    dependencies.go:60-62   (callers: internal/bft/view.go:834-838, 631-635,
+ *                                                    internal/bft/viewchanger.go:718)
+ *     VerifySignature       dependencies.go:63-64   (callers: viewchanger.go:598, 660, 983, 1022, 1076)
+ *     VerifyRequest         dependencies.go:58-59   (callers: internal/bft/controller.go:239, 742-745,
+ *                                                    internal/bft/requestpool.go:335-354)
+ *     VerifyProposal        dependencies.go:56-57   (caller: view.go:555 — bulk VerifyRequest site)
+ *   commit-vote collection  internal/bft/view.go:519-551 (processCommits), 827-849 (verifyVote),
+ *                           internal/bft/util.go:114-143 (voteSet), 183-187 (computeQuorum)
+ *   digests                 pkg/types/types.go:50-69 (Proposal.Digest), util.go:564-586
+ *
+ * A cgo (or any FFI) shim binds exactly these symbols; see INTEGRATION.md for the Go side.
+ *
+ * Conventions
+ *  - Return value: 0 on success, < 0 on ENGINE FAULT (CUDA error, out of memory, bad argument).  A
+ *    fault is never a verdict: the reference treats `error != nil` from a Verifier as "bad
+ *    signature" (view.go:839-842, 386-393), so a host shim must fail-stop on a negative return,
+ *    not convert it to a reject.
+ *  - Per-item verdicts go to caller-owned arrays: 1 = accept, 0 = reject.
+ *  - All pointers are HOST pointers unless the function name ends in _device.  Buffers are only
+ *    read during the call and never retained (cgo pointer rules).  Pinned (cudaHostAlloc /
+ *    cudaHostRegister) inputs are copied directly; pageable inputs are staged through the
+ *    engine's own pinned ring.
+ *  - Field elements and scalars are fixed-width big-endian: 32 bytes for P-256, 48 for P-384.
+ *  - Accept set = Go crypto/ecdsa (Verify / VerifyASN1): key must be an on-curve affine point with
+ *    coordinates < p; r, s in [1, n-1]; e = leftmost min(len, 32|48) digest bytes; R = (e/s)G +
+ *    (r/s)Q must not be infinity; accept iff R.x mod n == r.  No low-S rule.
+ *  - Thread-safe: calls on one engine serialise on an internal lock; the CUDA device is set
+ *    explicitly per call, so calls may come from any OS thread (cgo).
+ *  - There is no CPU fallback: without a usable CUDA device sbv_create fails.
+ */
+#ifndef SBV_H
+#define SBV_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sbv_engine sbv_engine;
+
+enum { SBV_P256 = 0, SBV_P384 = 1 };
+enum {
+    SBV_OK = 0,
+    SBV_ERR_ARG = -1,   /* bad argument */
+    SBV_ERR_CUDA = -2,  /* CUDA runtime / driver error */
+    SBV_ERR_NCCL = -3,  /* NCCL error (multi-device engines only) */
+    SBV_ERR_NOMEM = -4
+};
+
+/* n_devices in {1,2,4,8}; device_ordinals == NULL means 0..n_devices-1.  With n_devices > 1 the
+ * engine shards every batch across the devices and gathers the packed verdict bitmask with NCCL. */
+int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out);
+void sbv_destroy(sbv_engine *e);
+/* Human-readable description of the last fault on this engine (valid until the next call). */
+const char *sbv_last_error(const sbv_engine *e);
+int sbv_device_count(const sbv_engine *e);
+
+/* ECDSA verify, digests supplied.  SoA arrays of n fixed-width big-endian values. */
+int sbv_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *r, const uint8_t *s,
+                     const uint8_t *qx, const uint8_t *qy, const uint8_t *digest, uint8_t digest_len,
+                     uint8_t *ok);
+
+/* Same, with every input already resident on device `device_index` (0-based position in the
+ * engine's device list) and the verdicts left on the device.  Enqueued on `cuda_stream`
+ * (a cudaStream_t; NULL = the engine's own stream) and NOT synchronised. */
+int sbv_verify_batch_device(sbv_engine *e, int device_index, uint8_t curve, size_t n, const uint8_t *d_r,
+                            const uint8_t *d_s, const uint8_t *d_qx, const uint8_t *d_qy,
+                            const uint8_t *d_digest, uint8_t digest_len, uint8_t *d_ok, void *cuda_stream);
+
+/* DER front end: sigs = concatenated ASN.1 SEQUENCE{INTEGER r, INTEGER s}, sig_off[n+1].  Parsed
+ * with crypto/ecdsa.VerifyASN1 strictness (minimal lengths, minimal non-negative integers, no
+ * trailing bytes); malformed items reject.  qxy = n * (X||Y). */
+int sbv_verify_batch_der(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *sigs, const uint32_t *sig_off,
+                         const uint8_t *qxy, const uint8_t *digest, uint8_t digest_len, uint8_t *ok);
+
+/* SHA-256 over a ragged batch: msgs concatenated, msg_off[n+1] byte offsets.  digest_out = 32n. */
+int sbv_sha256_batch(sbv_engine *e, size_t n, const uint8_t *msgs, const uint64_t *msg_off, uint8_t *digest_out);
+
+/* Fused SHA-256 -> ECDSA verify (VerifyRequest / VerifySignature shape): the message digest never
+ * leaves the device.  digest_out may be NULL. */
+int sbv_hash_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *msgs, const uint64_t *msg_off,
+                          const uint8_t *r, const uint8_t *s, const uint8_t *qx, const uint8_t *qy,
+                          uint8_t *digest_out, uint8_t *ok);
+
+/* Mixed-curve batch: curve_tag[i] in {SBV_P256, SBV_P384}; every field is stored in a 48-byte
+ * slot (P-256 values right-aligned, i.e. 16 leading zero bytes); digest is 32 bytes per item. */
+int sbv_verify_mixed(sbv_engine *e, size_t n, const uint8_t *curve_tag, const uint8_t *r48, const uint8_t *s48,
+                     const uint8_t *qx48, const uint8_t *qy48, const uint8_t *digest32, uint8_t *ok);
+
+/* Distinct-signer quorum count per consensus instance (processCommits, view.go:519-551).
+ * Votes are given in arrival order.  A vote is registered iff signer == sender and sender !=
+ * self_id[instance] and the sender has no earlier registered vote in the instance
+ * (view.go:161-171, util.go:130-143); a registered vote is valid iff digest_match && ok
+ * (view.go:829-842).  valid_count[i] = number of valid votes; reached[i] = valid_count[i] >=
+ * threshold (the caller passes Quorum-1, view.go:531).  self_id may be NULL (no self filter). */
+int sbv_quorum(sbv_engine *e, size_t n_votes, const uint32_t *instance, const uint16_t *sender,
+               const uint16_t *signer, const uint8_t *digest_match, const uint8_t *ok, size_t n_instances,
+               const uint16_t *self_id, uint32_t threshold, uint32_t *valid_count, uint8_t *reached);
+
+/* computeQuorum(n) -> (q, f), internal/bft/util.go:183-187. */
+void sbv_compute_quorum(uint64_t n, uint32_t *q, uint32_t *f);
+
+/* Consenter key registry (ID -> public key) for the host-side Verifier mirror. */
+int sbv_set_keys(sbv_engine *e, uint64_t verification_seq, size_t n, const uint64_t *ids, const uint8_t *curve,
+                 const uint8_t *xy /* n * 96 bytes, 48-byte slots */);
+
+/* Introspection for benchmarks: number of kernel launches issued by this engine so far. */
+uint64_t sbv_kernel_launches(const sbv_engine *e);
+/* Peak-rate probe: dependent-free IMAD.WIDE.U32 loop on device 0; returns MAC32/s (0 on fault). */
+double sbv_probe_mad_rate(sbv_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBV_H */
