@@ -21,7 +21,7 @@ SYMBOLS = [
     "sbv_create", "sbv_destroy", "sbv_last_error", "sbv_device_count", "sbv_verify_batch",
     "sbv_verify_batch_device", "sbv_verify_batch_der", "sbv_sha256_batch", "sbv_hash_verify_batch",
     "sbv_verify_mixed", "sbv_quorum", "sbv_compute_quorum", "sbv_set_keys", "sbv_kernel_launches",
-    "sbv_probe_mad_rate",
+    "sbv_probe_mad_rate", "sbv_profile_enable", "sbv_profile_read",
 ]
 
 
@@ -109,6 +109,15 @@ class Engine:
 
     def probe_mad_rate(self) -> float:
         return float(self._lib.sbv_probe_mad_rate(self._h))
+
+    def profile_enable(self, on=True):
+        self._check(self._lib.sbv_profile_enable(self._h, C.c_int(1 if on else 0)), "sbv_profile_enable")
+
+    def profile_read(self):
+        """(prep_ms, verify_ms, n_launch_pairs) summed since the last read; synchronise first."""
+        p, v, k = C.c_double(), C.c_double(), C.c_uint64()
+        self._check(self._lib.sbv_profile_read(self._h, C.byref(p), C.byref(v), C.byref(k)), "sbv_profile_read")
+        return p.value, v.value, k.value
 
     # ---- host-buffer API (numpy arrays, or anything exposing a host pointer via .ctypes) ----
     def verify_batch(self, curve, r, s, qx, qy, digest, out=None) -> np.ndarray:

@@ -13,73 +13,13 @@
 #include <string>
 #include <vector>
 
-#include "../../include/sbv.h"
-#include "kernels.cuh"
+#include "engine.h"
 #include "sha256.cuh"
 #include "quorum.cuh"
 
 using namespace sbv;
 
 namespace {
-
-struct Dev {
-    int ordinal = 0;
-    cudaStream_t stream = nullptr;
-    uint32_t *gtab[2] = {nullptr, nullptr};
-    // per-batch workspace (device)
-    size_t cap = 0;
-    uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr, *d_qy = nullptr, *d_dig = nullptr, *d_ok = nullptr;
-    uint8_t *d_gidx = nullptr, *d_flags = nullptr;
-    int8_t *d_digits = nullptr;
-    // message workspace
-    size_t msg_cap = 0, off_cap = 0;
-    uint8_t *d_msgs = nullptr;
-    uint64_t *d_off = nullptr;
-    // pinned staging
-    uint8_t *h_pin = nullptr;
-    size_t h_pin_cap = 0;
-    // generic scratch (quorum, bitmask)
-    uint8_t *d_scratch = nullptr;
-    size_t scratch_cap = 0;
-};
-
-}  // namespace
-
-struct sbv_engine {
-    std::vector<Dev> devs;
-    std::mutex mu;
-    std::string err;
-    uint64_t launches = 0;
-    int p256_w = 4, p256_block = 128, p384_w = 3, p384_block = 128;
-    // NCCL (multi-device only; loaded lazily with dlopen so single-device users never touch it)
-    void *nccl_lib = nullptr;
-    std::vector<void *> nccl_comms;
-    // key registry
-    uint64_t verification_seq = 0;
-    std::vector<uint64_t> key_ids;
-    std::vector<uint8_t> key_curve;
-    std::vector<uint8_t> key_xy;
-};
-
-namespace {
-
-int fail(sbv_engine *e, int code, const char *fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    if (e) e->err = buf;
-    return code;
-}
-
-#define CU(e, call)                                                                               \
-    do {                                                                                          \
-        cudaError_t _st = (call);                                                                 \
-        if (_st != cudaSuccess)                                                                   \
-            return fail(e, SBV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), \
-                        __FILE__, __LINE__);                                                      \
-    } while (0)
 
 int env_int(const char *name, int dflt) {
     const char *v = getenv(name);
@@ -119,7 +59,9 @@ int ensure_pinned(sbv_engine *e, Dev &d, size_t bytes) {
     return 0;
 }
 
-int ensure_scratch(sbv_engine *e, Dev &d, size_t bytes) {
+int ensure_scratch(sbv_engine *e, Dev &d, size_t bytes) { return sbv_ensure_scratch(e, d, bytes); }
+}  // namespace
+int sbv_ensure_scratch(sbv_engine *e, Dev &d, size_t bytes) {
     if (bytes <= d.scratch_cap) return 0;
     CU(e, cudaSetDevice(d.ordinal));
     if (d.d_scratch) cudaFree(d.d_scratch);
@@ -129,6 +71,7 @@ int ensure_scratch(sbv_engine *e, Dev &d, size_t bytes) {
     d.scratch_cap = cap;
     return 0;
 }
+namespace {
 
 int ensure_msgs(sbv_engine *e, Dev &d, size_t bytes, size_t n_off) {
     CU(e, cudaSetDevice(d.ordinal));
@@ -170,39 +113,17 @@ int h2d(sbv_engine *e, Dev &d, void *dst, const void *src, size_t bytes, size_t 
     return 0;
 }
 
-template <class C, int W, int BLOCK>
-int launch_verify_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
-                    const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st,
-                    int curve_idx) {
-    constexpr int S = 8;
-    constexpr int TE = Windows<32 * C::N, W>::ENTRIES;
-    const uint32_t nn = (uint32_t)n;
-    uint32_t pthreads = (nn + S - 1) / S;
-    uint32_t pblocks = (pthreads + 127) / 128;
-    k_prep<C, W, S><<<pblocks, 128, 0, st>>>(nn, d_r, d_s, d_dig, dlen, d.d_gidx, d.d_digits, d.d_flags);
-    size_t smem = (size_t)TE * 3 * C::N * 4 * BLOCK;
-    static bool attr_set[8] = {false};
-    (void)attr_set;
-    CU(e, cudaFuncSetAttribute(k_verify<C, W, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint32_t vblocks = (nn + BLOCK - 1) / BLOCK;
-    k_verify<C, W, BLOCK><<<vblocks, BLOCK, smem, st>>>(nn, d_qx, d_qy, d_r, d.d_gidx, d.d_digits, d.d_flags,
-                                                        reinterpret_cast<const uint4 *>(d.gtab[curve_idx]), d_ok);
-    e->launches += 2;
-    CU(e, cudaGetLastError());
-    return 0;
-}
-
 // inputs on device d; enqueues on st; no sync
 int launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_r, const uint8_t *d_s,
                   const uint8_t *d_qx, const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok,
                   cudaStream_t st) {
     if (n == 0) return 0;
     if (curve == SBV_P256) {
-        if (e->p256_w == 3) return launch_verify_t<P256, 3, 128>(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st, 0);
-        if (e->p256_block == 64) return launch_verify_t<P256, 4, 64>(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st, 0);
-        return launch_verify_t<P256, 4, 128>(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st, 0);
+        if (e->p256_w == 3) return sbv_launch_p256_w3_b128(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
+        if (e->p256_block == 64) return sbv_launch_p256_w4_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
+        return sbv_launch_p256_w4_b128(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
     }
-    return launch_verify_t<P384, 3, 128>(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st, 1);
+    return sbv_launch_p384_w3_b128(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
 }
 
 __global__ void k_mad_probe(uint32_t *out, uint32_t iters) {
@@ -246,14 +167,7 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
         d.ordinal = device_ordinals ? device_ordinals[g] : g;
         cudaError_t st = cudaSetDevice(d.ordinal);
         if (st == cudaSuccess) st = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
-        if (st == cudaSuccess) st = cudaMalloc(&d.gtab[0], (size_t)32 * 256 * 16 * 4);
-        if (st == cudaSuccess) st = cudaMalloc(&d.gtab[1], (size_t)48 * 256 * 24 * 4);
-        if (st == cudaSuccess) {
-            k_gtable_init<P256><<<32 * 256 / 128, 128, 0, d.stream>>>(d.gtab[0]);
-            k_gtable_init<P384><<<48 * 256 / 128, 128, 0, d.stream>>>(d.gtab[1]);
-            e->launches += 2;
-            st = cudaStreamSynchronize(d.stream);
-        }
+        if (st == cudaSuccess && sbv_init_gtables(e, d) != 0) st = cudaErrorUnknown;
         if (st != cudaSuccess) {
             fprintf(stderr, "sbv_create: device %d: %s\n", d.ordinal, cudaGetErrorString(st));
             sbv_destroy(e);
@@ -301,7 +215,7 @@ int sbv_verify_batch_device(sbv_engine *e, int device_index, uint8_t curve, size
     CU(e, cudaSetDevice(d.ordinal));
     int rc = ensure_workspace(e, d, n);
     if (rc) return rc;
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : d.stream;
+    cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL = the legacy default stream
     return launch_verify(e, d, curve, n, d_r, d_s, d_qx, d_qy, d_digest, digest_len, d_ok, st);
 }
 
@@ -374,3 +288,39 @@ double sbv_probe_mad_rate(sbv_engine *e) {
 }  // extern "C"
 
 #include "engine_more.inc"
+
+// ---- profiling hooks (bench.py's roofline leg): CUDA-event timing of the prep / verify kernels ----
+extern "C" {
+
+int sbv_profile_enable(sbv_engine *e, int on) {
+    if (!e) return SBV_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->profiling = on != 0;
+    for (Dev &d : e->devs) d.prof_used = 0;
+    return SBV_OK;
+}
+
+// Sums the recorded intervals (all devices), then resets.  Caller must have synchronised the streams.
+int sbv_profile_read(sbv_engine *e, double *prep_ms, double *verify_ms, uint64_t *n_pairs) {
+    if (!e) return SBV_ERR_ARG;
+    std::lock_guard<std::mutex> lk(e->mu);
+    double p = 0, v = 0;
+    uint64_t cnt = 0;
+    for (Dev &d : e->devs) {
+        CU(e, cudaSetDevice(d.ordinal));
+        for (size_t i = 0; i + 2 < d.prof_used + 0 && i + 2 < d.prof_events.size(); i += 3) {
+            float a = 0, b = 0;
+            CU(e, cudaEventSynchronize(d.prof_events[i + 2]));
+            CU(e, cudaEventElapsedTime(&a, d.prof_events[i], d.prof_events[i + 1]));
+            CU(e, cudaEventElapsedTime(&b, d.prof_events[i + 1], d.prof_events[i + 2]));
+            p += a; v += b; cnt++;
+        }
+        d.prof_used = 0;
+    }
+    if (prep_ms) *prep_ms = p;
+    if (verify_ms) *verify_ms = v;
+    if (n_pairs) *n_pairs = cnt;
+    return SBV_OK;
+}
+
+}  // extern "C"

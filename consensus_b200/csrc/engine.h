@@ -1,0 +1,84 @@
+// engine.h — shared host-side state of libsbv.so (one engine = 1..8 devices of one box).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sbv.h"
+
+struct Dev {
+    int ordinal = 0;
+    cudaStream_t stream = nullptr;
+    uint32_t *gtab[2] = {nullptr, nullptr};
+    // per-batch workspace (device)
+    size_t cap = 0;
+    uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr, *d_qy = nullptr, *d_dig = nullptr, *d_ok = nullptr;
+    uint8_t *d_gidx = nullptr, *d_flags = nullptr;
+    int8_t *d_digits = nullptr;
+    // message workspace
+    size_t msg_cap = 0, off_cap = 0;
+    uint8_t *d_msgs = nullptr;
+    uint64_t *d_off = nullptr;
+    // pinned staging
+    uint8_t *h_pin = nullptr;
+    size_t h_pin_cap = 0;
+    // generic scratch (quorum, bitmask)
+    uint8_t *d_scratch = nullptr;
+    size_t scratch_cap = 0;
+    // profiling: event pairs around the prep / verify kernels (only when enabled)
+    std::vector<cudaEvent_t> prof_events;  // triples: before prep, between, after verify
+    size_t prof_used = 0;
+};
+
+struct sbv_engine {
+    std::vector<Dev> devs;
+    std::mutex mu;
+    std::string err;
+    uint64_t launches = 0;
+    int p256_w = 4, p256_block = 128, p384_w = 3, p384_block = 128;
+    bool profiling = false;
+    // NCCL (multi-device only; loaded lazily with dlopen so single-device users never touch it)
+    void *nccl_lib = nullptr;
+    std::vector<void *> nccl_comms;
+    // key registry
+    uint64_t verification_seq = 0;
+    std::vector<uint64_t> key_ids;
+    std::vector<uint8_t> key_curve;
+    std::vector<uint8_t> key_xy;
+};
+
+inline int sbv_fail(sbv_engine *e, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (e) e->err = buf;
+    return code;
+}
+#define fail sbv_fail
+
+#define CU(e, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t _st = (call);                                                                     \
+        if (_st != cudaSuccess)                                                                       \
+            return sbv_fail(e, SBV_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), \
+                            __FILE__, __LINE__);                                                      \
+    } while (0)
+
+// per-(curve, window, block) kernel launchers — one translation unit each (inst_*.cu)
+int sbv_launch_p256_w4_b128(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
+                            const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
+int sbv_launch_p256_w4_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
+                           const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
+int sbv_launch_p256_w3_b128(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
+                            const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
+int sbv_launch_p384_w3_b128(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
+                            const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
+int sbv_init_gtables(sbv_engine *e, Dev &d);  // gtable.cu
+int sbv_ensure_scratch(sbv_engine *e, Dev &d, size_t bytes);

@@ -238,19 +238,21 @@ __global__ void __launch_bounds__(BLOCK) k_verify(uint32_t n, const uint8_t *__r
             for (int i = 0; i < N; i++) { x2[i] = TAB(e, 0, i); y2[i] = TAB(e, 1, i); z2[i] = TAB(e, 2, i); }
             pt_add<C, false>(acc, x2, y2, z2, neg, skip);
         }
-        if (win < C::BYTES) {
-            uint32_t b = gidx[(size_t)win * n + idx];
-            const uint4 *src = gtab + ((size_t)win * 256 + b) * (2 * N / 4);
-            uint32_t x2[N], y2[N];
+    }
+    // u1*G from the fixed-base comb: BYTES complete points, added after the last doubling
+#pragma unroll 1
+    for (int win = 0; win < C::BYTES; win++) {
+        uint32_t b = gidx[(size_t)win * n + idx];
+        const uint4 *src = gtab + ((size_t)win * 256 + b) * (2 * N / 4);
+        uint32_t x2[N], y2[N];
 #pragma unroll
-            for (int i = 0; i < N / 4; i++) {
-                uint4 v = __ldg(src + i);
-                x2[4 * i] = v.x; x2[4 * i + 1] = v.y; x2[4 * i + 2] = v.z; x2[4 * i + 3] = v.w;
-                uint4 u = __ldg(src + N / 4 + i);
-                y2[4 * i] = u.x; y2[4 * i + 1] = u.y; y2[4 * i + 2] = u.z; y2[4 * i + 3] = u.w;
-            }
-            pt_add<C, true>(acc, x2, y2, one, false, b == 0);
+        for (int i = 0; i < N / 4; i++) {
+            uint4 v = __ldg(src + i);
+            x2[4 * i] = v.x; x2[4 * i + 1] = v.y; x2[4 * i + 2] = v.z; x2[4 * i + 3] = v.w;
+            uint4 u = __ldg(src + N / 4 + i);
+            y2[4 * i] = u.x; y2[4 * i + 1] = u.y; y2[4 * i + 2] = u.z; y2[4 * i + 3] = u.w;
         }
+        pt_add<C, true>(acc, x2, y2, one, false, b == 0);
     }
 #undef TAB
     // accept iff R != inf and R.x mod n == r  <=>  X == r*Z^2 or (r + n < p and X == (r+n)*Z^2)

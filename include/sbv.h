@@ -68,7 +68,7 @@ int sbv_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *r, c
 
 /* Same, with every input already resident on device `device_index` (0-based position in the
  * engine's device list) and the verdicts left on the device.  Enqueued on `cuda_stream`
- * (a cudaStream_t; NULL = the engine's own stream) and NOT synchronised. */
+ * (a cudaStream_t; NULL = the legacy default stream) and NOT synchronised. */
 int sbv_verify_batch_device(sbv_engine *e, int device_index, uint8_t curve, size_t n, const uint8_t *d_r,
                             const uint8_t *d_s, const uint8_t *d_qx, const uint8_t *d_qy,
                             const uint8_t *d_digest, uint8_t digest_len, uint8_t *d_ok, void *cuda_stream);
@@ -112,6 +112,11 @@ int sbv_set_keys(sbv_engine *e, uint64_t verification_seq, size_t n, const uint6
 
 /* Introspection for benchmarks: number of kernel launches issued by this engine so far. */
 uint64_t sbv_kernel_launches(const sbv_engine *e);
+/* Optional CUDA-event timing of the two kernels of every verify launch (off by default).
+ * sbv_profile_read sums the recorded intervals in milliseconds over all devices and resets; the
+ * caller synchronises the streams it used first. */
+int sbv_profile_enable(sbv_engine *e, int on);
+int sbv_profile_read(sbv_engine *e, double *prep_ms, double *verify_ms, uint64_t *n_launch_pairs);
 /* Peak-rate probe: dependent-free IMAD.WIDE.U32 loop on device 0; returns MAC32/s (0 on fault). */
 double sbv_probe_mad_rate(sbv_engine *e);
 

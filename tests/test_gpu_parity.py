@@ -25,7 +25,7 @@ def _be(v, L):
 
 
 def test_rfc6979_vectors(eng):
-    from tests.test_oracle import RFC6979
+    from vectors import RFC6979
     for curve, ux, uy, msg, r, s in RFC6979:
         L = 32 if curve == P256 else 48
         dig = np.frombuffer(hashlib.sha256(msg).digest(), np.uint8)
