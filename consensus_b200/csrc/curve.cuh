@@ -14,6 +14,10 @@ namespace sbv {
 // no multiplications: per 64-bit step the quotient digit is the low limb pair itself and
 // q*p = q*2^256 - q*2^224 + q*2^192 + q*2^96 - q is four shifted adds.
 // -------------------------------------------------------------------------------------------------
+struct Fe8 { uint32_t v[8]; };
+static __device__ __noinline__ Fe8 p256_fmul_call(Fe8 a, Fe8 b);
+static __device__ __noinline__ Fe8 p256_fsqr_call(Fe8 a);
+
 struct P256 {
     static constexpr int N = 8;
     static constexpr int BYTES = 32;
@@ -63,12 +67,43 @@ struct P256 {
         bool use_t = (t16 != 0) || (bw == 0);
         mp_select<8>(r, use_t, t, hi);
     }
-    SBV_DEV static void fmul(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    SBV_DEV static void fmul_inline(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
         uint32_t T[16];
         mp_mul<8>(T, a, b);
         redc(r, T);
     }
-    SBV_DEV static void fsqr(uint32_t (&r)[8], const uint32_t (&a)[8]) { fmul(r, a, a); }
+    SBV_DEV static void fsqr_inline(uint32_t (&r)[8], const uint32_t (&a)[8]) {
+        uint32_t T[16];
+        mp_sqr<8>(T, a);
+        redc(r, T);
+    }
+    // Out of line on purpose: the whole verify loop then fits the instruction cache.  Operands and
+    // result travel in registers (by-value struct ABI), so a call costs moves, not memory traffic.
+    SBV_DEV static void fmul(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+        Fe8 x, y;
+        mp_copy<8>(x.v, a); mp_copy<8>(y.v, b);
+        Fe8 z = p256_fmul_call(x, y);
+        mp_copy<8>(r, z.v);
+    }
+    SBV_DEV static void fsqr(uint32_t (&r)[8], const uint32_t (&a)[8]) {
+        Fe8 x;
+        mp_copy<8>(x.v, a);
+        Fe8 z = p256_fsqr_call(x);
+        mp_copy<8>(r, z.v);
+    }
+    // r = a/2 mod p
+    SBV_DEV static void fhalf(uint32_t (&r)[8], const uint32_t (&a)[8]) {
+        const uint32_t p[8] = SBV_P256_P;
+        const uint32_t mask = 0u - (a[0] & 1u);
+        uint32_t t[8];
+        t[0] = add_cc(a[0], p[0] & mask);
+#pragma unroll
+        for (int i = 1; i < 8; i++) t[i] = addc_cc(a[i], p[i] & mask);
+        const uint32_t top = addc(0, 0);
+#pragma unroll
+        for (int i = 0; i < 7; i++) r[i] = __funnelshift_r(t[i], t[i + 1], 1);
+        r[7] = __funnelshift_r(t[7], top, 1);
+    }
     SBV_DEV static void fadd(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
         const uint32_t p[8] = SBV_P256_P;
         mod_add<8>(r, a, b, p);
@@ -82,6 +117,17 @@ struct P256 {
         mont_mul_generic<8>(r, a, b, n, SBV_P256_NINV);
     }
 };
+
+static __device__ __noinline__ Fe8 p256_fmul_call(Fe8 a, Fe8 b) {
+    Fe8 r;
+    P256::fmul_inline(r.v, a.v, b.v);
+    return r;
+}
+static __device__ __noinline__ Fe8 p256_fsqr_call(Fe8 a) {
+    Fe8 r;
+    P256::fsqr_inline(r.v, a.v);
+    return r;
+}
 
 // -------------------------------------------------------------------------------------------------
 // P-384: generic word-serial Montgomery for both fields (12 limbs).
@@ -108,6 +154,18 @@ struct P384 {
         mont_mul_generic<12>(r, a, b, p, SBV_P384_PINV);
     }
     SBV_DEV static void fsqr(uint32_t (&r)[12], const uint32_t (&a)[12]) { fmul(r, a, a); }
+    SBV_DEV static void fhalf(uint32_t (&r)[12], const uint32_t (&a)[12]) {
+        const uint32_t p[12] = SBV_P384_P;
+        const uint32_t mask = 0u - (a[0] & 1u);
+        uint32_t t[12];
+        t[0] = add_cc(a[0], p[0] & mask);
+#pragma unroll
+        for (int i = 1; i < 12; i++) t[i] = addc_cc(a[i], p[i] & mask);
+        const uint32_t top = addc(0, 0);
+#pragma unroll
+        for (int i = 0; i < 11; i++) r[i] = __funnelshift_r(t[i], t[i + 1], 1);
+        r[11] = __funnelshift_r(t[11], top, 1);
+    }
     SBV_DEV static void fadd(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
         const uint32_t p[12] = SBV_P384_P;
         mod_add<12>(r, a, b, p);
@@ -130,33 +188,32 @@ struct Jac {
     uint32_t X[C::N], Y[C::N], Z[C::N];
 };
 
-// a = -3 doubling, 4M + 4S.  Infinity (Z = 0) maps to infinity; Y = 0 cannot occur (odd order).
+// a = -3 doubling, 4M + 4S, 9 add/sub + 1 halving.  Infinity (Z = 0) maps to infinity; Y = 0
+// cannot occur (odd group order).
+//   S = 2Y, Z3 = S*Z, B = S^2 = 4Y^2, beta4 = X*B = 4XY^2, C = B^2/2 = 8Y^4,
+//   alpha = 3(X - Z^2)(X + Z^2), X3 = alpha^2 - 2*beta4, Y3 = alpha*(beta4 - X3) - C
 template <class C>
 SBV_DEV void pt_double(Jac<C> &P) {
     constexpr int N = C::N;
-    uint32_t delta[N], gamma[N], beta[N], alpha[N], t1[N], t2[N];
+    uint32_t delta[N], s[N], bb[N], beta4[N], alpha[N], t1[N], t2[N];
     C::fsqr(delta, P.Z);
-    C::fsqr(gamma, P.Y);
-    C::fmul(beta, P.X, gamma);
+    C::fadd(s, P.Y, P.Y);
+    C::fmul(P.Z, s, P.Z);       // Z3 = 2 Y Z
+    C::fsqr(bb, s);             // 4 Y^2
+    C::fmul(beta4, P.X, bb);    // 4 X Y^2
+    C::fsqr(t1, bb);            // 16 Y^4
+    C::fhalf(bb, t1);           // 8 Y^4
     C::fsub(t1, P.X, delta);
     C::fadd(t2, P.X, delta);
     C::fmul(alpha, t1, t2);
     C::fadd(t1, alpha, alpha);
-    C::fadd(alpha, t1, alpha);  // alpha = 3 (X - delta)(X + delta)
-    C::fmul(t1, P.Y, P.Z);
-    C::fadd(P.Z, t1, t1);       // Z3 = 2 Y Z
-    C::fadd(beta, beta, beta);
-    C::fadd(beta, beta, beta);  // 4 beta
+    C::fadd(alpha, t1, alpha);  // 3 (X - delta)(X + delta)
     C::fsqr(t1, alpha);
-    C::fadd(t2, beta, beta);    // 8 beta
-    C::fsub(P.X, t1, t2);       // X3 = alpha^2 - 8 beta
-    C::fsub(t1, beta, P.X);
+    C::fadd(t2, beta4, beta4);
+    C::fsub(P.X, t1, t2);       // X3
+    C::fsub(t1, beta4, P.X);
     C::fmul(t2, alpha, t1);
-    C::fsqr(t1, gamma);
-    C::fadd(t1, t1, t1);
-    C::fadd(t1, t1, t1);
-    C::fadd(t1, t1, t1);        // 8 gamma^2
-    C::fsub(P.Y, t2, t1);
+    C::fsub(P.Y, t2, bb);       // Y3
 }
 
 // P += (x2, y2[, z2]).  AFFINE: z2 == 1 (mixed add, 8M+3S) else general (12M+4S).

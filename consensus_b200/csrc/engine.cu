@@ -119,9 +119,9 @@ int launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t 
                   cudaStream_t st) {
     if (n == 0) return 0;
     if (curve == SBV_P256) {
-        if (e->p256_w == 3) return sbv_launch_p256_w3_b128(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
-        if (e->p256_block == 64) return sbv_launch_p256_w4_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
-        return sbv_launch_p256_w4_b128(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
+        if (e->p256_w == 4) return sbv_launch_p256_w4_b128(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
+        if (e->p256_block == 128) return sbv_launch_p256_w3_b128(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
+        return sbv_launch_p256_w3_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
     }
     return sbv_launch_p384_w3_b128(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
 }
@@ -159,8 +159,8 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count < n_devices) return SBV_ERR_CUDA;
     sbv_engine *e = new sbv_engine();
-    e->p256_w = env_int("SBV_P256_W", 4);
-    e->p256_block = env_int("SBV_P256_BLOCK", 128);
+    e->p256_w = env_int("SBV_P256_W", 3);
+    e->p256_block = env_int("SBV_P256_BLOCK", 64);
     e->devs.resize(n_devices);
     for (int g = 0; g < n_devices; g++) {
         Dev &d = e->devs[g];

@@ -165,8 +165,8 @@ __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
-template <class C, int W, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_verify(uint32_t n, const uint8_t *__restrict__ qx_be, const uint8_t *__restrict__ qy_be,
+template <class C, int W, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_verify(uint32_t n, const uint8_t *__restrict__ qx_be, const uint8_t *__restrict__ qy_be,
                                                   const uint8_t *__restrict__ r_be, const uint8_t *__restrict__ gidx,
                                                   const int8_t *__restrict__ digits, const uint8_t *__restrict__ flags,
                                                   const uint4 *__restrict__ gtab, uint8_t *__restrict__ ok_out) {

@@ -5,7 +5,7 @@
 
 namespace sbv {
 
-template <class C, int W, int BLOCK>
+template <class C, int W, int BLOCK, int MINB>
 int launch_verify_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                     const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st,
                     int curve_idx) {
@@ -30,11 +30,11 @@ int launch_verify_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const u
     const size_t smem = (size_t)TE * 3 * C::N * 4 * BLOCK;
     static bool attr_done = false;
     if (!attr_done) {
-        CU(e, cudaFuncSetAttribute(k_verify<C, W, BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(e, cudaFuncSetAttribute(k_verify<C, W, BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
     const uint32_t vblocks = (nn + BLOCK - 1) / BLOCK;
-    k_verify<C, W, BLOCK><<<vblocks, BLOCK, smem, st>>>(nn, d_qx, d_qy, d_r, d.d_gidx, d.d_digits, d.d_flags,
+    k_verify<C, W, BLOCK, MINB><<<vblocks, BLOCK, smem, st>>>(nn, d_qx, d_qy, d_r, d.d_gidx, d.d_digits, d.d_flags,
                                                         reinterpret_cast<const uint4 *>(d.gtab[curve_idx]), d_ok);
     if (ev) CU(e, cudaEventRecord(ev[2], st));
     e->launches += 2;
@@ -44,8 +44,8 @@ int launch_verify_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const u
 
 }  // namespace sbv
 
-#define SBV_DEFINE_LAUNCHER(NAME, CURVE, W, BLOCK, IDX)                                                                  \
+#define SBV_DEFINE_LAUNCHER(NAME, CURVE, W, BLOCK, MINB, IDX)                                                                 \
     int NAME(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,               \
              const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st) {                 \
-        return sbv::launch_verify_t<sbv::CURVE, W, BLOCK>(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st, IDX);    \
+        return sbv::launch_verify_t<sbv::CURVE, W, BLOCK, MINB>(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st, IDX); \
     }

@@ -66,6 +66,55 @@ SBV_DEV void mp_mul(uint32_t (&r)[2 * N], const uint32_t (&a)[N], const uint32_t
     r[2 * N - 1] = addc(E[2 * N - 1], O[2 * N - 2]);
 }
 
+// r[0..2N) = a^2 : off-diagonal products once (even/odd split as in mp_mul), doubled, plus the diagonal.
+// N(N-1)/2 + N wide MADs instead of N^2.
+template <int N>
+SBV_DEV void mp_sqr(uint32_t (&r)[2 * N], const uint32_t (&a)[N]) {
+    static_assert(N % 2 == 0, "even limb count");
+    uint32_t E[2 * N], O[2 * N];  // O[k] has weight 2^(32(k+1))
+#pragma unroll
+    for (int i = 0; i < 2 * N; i++) { E[i] = 0; O[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < N - 1; i++) {
+        // j > i, same parity as i  -> E at limb i+j
+        if (i + 2 < N) {
+            mad_wide_cc(E[2 * i + 2], E[2 * i + 3], a[i], a[i + 2]);
+#pragma unroll
+            for (int j = i + 4; j < N; j += 2) madc_wide_cc(E[i + j], E[i + j + 1], a[i], a[j]);
+            // last j of this row: N-2 or N-1 (same parity as i)
+            constexpr int dummy = 0; (void)dummy;
+            const int jl = ((N - 1 - i) % 2 == 0) ? N - 1 : N - 2;
+            if (i + jl + 2 < 2 * N) E[i + jl + 2] = addc(E[i + jl + 2], 0);
+        }
+        // j > i, opposite parity -> O at index i+j-1
+        mad_wide_cc(O[2 * i], O[2 * i + 1], a[i], a[i + 1]);
+#pragma unroll
+        for (int j = i + 3; j < N; j += 2) madc_wide_cc(O[i + j - 1], O[i + j], a[i], a[j]);
+        {
+            const int jl = ((N - 1 - i) % 2 == 1) ? N - 1 : N - 2;
+            if (i + jl + 1 < 2 * N) O[i + jl + 1] = addc(O[i + jl + 1], 0);
+        }
+    }
+    // T = E + (O << 32)
+    uint32_t T[2 * N];
+    T[0] = E[0];
+    T[1] = add_cc(E[1], O[0]);
+#pragma unroll
+    for (int i = 2; i < 2 * N - 1; i++) T[i] = addc_cc(E[i], O[i - 1]);
+    T[2 * N - 1] = addc(E[2 * N - 1], O[2 * N - 2]);
+    // T = 2T
+    T[0] = add_cc(T[0], T[0]);
+#pragma unroll
+    for (int i = 1; i < 2 * N - 1; i++) T[i] = addc_cc(T[i], T[i]);
+    T[2 * N - 1] = addc(T[2 * N - 1], T[2 * N - 1]);
+    // T += sum a_i^2 * 2^(64 i)
+    mad_wide_cc(T[0], T[1], a[0], a[0]);
+#pragma unroll
+    for (int i = 1; i < N; i++) madc_wide_cc(T[2 * i], T[2 * i + 1], a[i], a[i]);
+#pragma unroll
+    for (int i = 0; i < 2 * N; i++) r[i] = T[i];
+}
+
 // r = a + b, returns carry-out
 template <int N>
 SBV_DEV uint32_t mp_add(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&b)[N]) {

@@ -14,7 +14,7 @@ dev = torch.device("cuda:0")
 t = {k: torch.from_numpy(b[k]).to(dev) for k in ("r", "s", "qx", "qy", "digest")}
 ok = torch.zeros(n, dtype=torch.uint8, device=dev)
 res = {}
-for w, blk in [(4, 128), (4, 64), (3, 128)]:
+for w, blk in [(3, 64), (3, 128), (4, 128)]:
     os.environ["SBV_P256_W"] = str(w); os.environ["SBV_P256_BLOCK"] = str(blk)
     e = sbv.Engine(n_devices=1)
     if "mad" not in res:
