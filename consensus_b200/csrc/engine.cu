@@ -142,10 +142,99 @@ __global__ void k_mad_probe(uint32_t *out, uint32_t iters) {
     if (s == 0x1234567) out[0] = (uint32_t)s;
 }
 
+
+// ---- NCCL, loaded with dlopen only by multi-device engines ----
+typedef int (*nccl_comm_init_all_t)(void **comms, int ndev, const int *devlist);
+typedef int (*nccl_comm_destroy_t)(void *comm);
+typedef int (*nccl_group_t)(void);
+typedef int (*nccl_all_gather_t)(const void *send, void *recv, size_t count, int dtype, void *comm, cudaStream_t st);
+typedef const char *(*nccl_err_t)(int);
+struct NcclApi {
+    nccl_comm_init_all_t comm_init_all = nullptr;
+    nccl_comm_destroy_t comm_destroy = nullptr;
+    nccl_group_t group_start = nullptr, group_end = nullptr;
+    nccl_all_gather_t all_gather = nullptr;
+    nccl_err_t err_string = nullptr;
+} g_nccl;
+constexpr int NCCL_UINT32 = 3;  // ncclUint32
+
+int nccl_load(sbv_engine *e) {
+    if (e->nccl_lib) return 0;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) return fail(e, SBV_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    g_nccl.comm_init_all = (nccl_comm_init_all_t)dlsym(h, "ncclCommInitAll");
+    g_nccl.comm_destroy = (nccl_comm_destroy_t)dlsym(h, "ncclCommDestroy");
+    g_nccl.group_start = (nccl_group_t)dlsym(h, "ncclGroupStart");
+    g_nccl.group_end = (nccl_group_t)dlsym(h, "ncclGroupEnd");
+    g_nccl.all_gather = (nccl_all_gather_t)dlsym(h, "ncclAllGather");
+    g_nccl.err_string = (nccl_err_t)dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.comm_init_all || !g_nccl.comm_destroy || !g_nccl.group_start || !g_nccl.group_end || !g_nccl.all_gather)
+        return fail(e, SBV_ERR_NCCL, "libnccl lacks a required symbol");
+    e->nccl_lib = h;
+    return 0;
+}
+#define NC(e, call)                                                                                       \
+    do {                                                                                                  \
+        int _r = (call);                                                                                  \
+        if (_r != 0)                                                                                      \
+            return fail(e, SBV_ERR_NCCL, "%s failed: %s", #call, g_nccl.err_string ? g_nccl.err_string(_r) : "?"); \
+    } while (0)
+
 struct Shard { size_t lo, n; };
 Shard shard_of(size_t n, int g, int G) {
     size_t lo = n * g / G, hi = n * (g + 1) / G;
     return {lo, hi - lo};
+}
+
+
+// Multi-device epilogue: every device packs its shard's verdict bytes into a bitmask
+// (k_pack_bits), one ncclAllGather (in place, on each device's compute stream, right behind its
+// verify kernel) assembles the whole mask on every device, and device 0 returns it to the host in
+// a single n/8-byte copy.  Shards are padded to a common word count, so device g's words start at
+// g * words_per.
+size_t words_per_shard(size_t n, int G) { return (((n + G - 1) / G) + 31) / 32; }
+
+int gather_verdicts(sbv_engine *e, size_t n, uint8_t *ok_host) {
+    const int G = (int)e->devs.size();
+    const size_t wp = words_per_shard(n, G);
+    for (int g = 0; g < G; g++) {
+        Dev &d = e->devs[g];
+        CU(e, cudaSetDevice(d.ordinal));
+        int rc = sbv_ensure_scratch(e, d, wp * G * 4);
+        if (rc) return rc;
+        Shard sh = shard_of(n, g, G);
+        uint32_t *mine = (uint32_t *)d.d_scratch + wp * g;
+        CU(e, cudaMemsetAsync(mine, 0, wp * 4, d.stream));
+        if (sh.n) {
+            k_pack_bits<<<(uint32_t)((sh.n + 255) / 256), 256, 0, d.stream>>>((uint32_t)sh.n, d.d_ok, mine);
+            e->launches += 1;
+            CU(e, cudaGetLastError());
+        }
+    }
+    NC(e, g_nccl.group_start());
+    for (int g = 0; g < G; g++) {
+        Dev &d = e->devs[g];
+        uint32_t *buf = (uint32_t *)d.d_scratch;
+        NC(e, g_nccl.all_gather(buf + wp * g, buf, wp, NCCL_UINT32, e->nccl_comms[g], d.stream));
+    }
+    NC(e, g_nccl.group_end());
+    Dev &d0 = e->devs[0];
+    CU(e, cudaSetDevice(d0.ordinal));
+    (void)ok_host;
+    e->gather_words.resize(wp * G);
+    CU(e, cudaMemcpyAsync(e->gather_words.data(), d0.d_scratch, wp * G * 4, cudaMemcpyDeviceToHost, d0.stream));
+    return 0;
+}
+
+void unpack_verdicts(sbv_engine *e, size_t n, uint8_t *ok_host) {
+    const int G = (int)e->devs.size();
+    const size_t wp = words_per_shard(n, G);
+    for (int g = 0; g < G; g++) {
+        Shard sh = shard_of(n, g, G);
+        const uint32_t *w = e->gather_words.data() + wp * g;
+        for (size_t i = 0; i < sh.n; i++) ok_host[sh.lo + i] = (w[i >> 5] >> (i & 31)) & 1u;
+    }
 }
 
 }  // namespace
@@ -174,12 +263,24 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
             return SBV_ERR_CUDA;
         }
     }
+    if (n_devices > 1) {
+        std::vector<int> ords;
+        for (Dev &d : e->devs) ords.push_back(d.ordinal);
+        e->nccl_comms.assign(n_devices, nullptr);
+        if (nccl_load(e) != 0 || g_nccl.comm_init_all(e->nccl_comms.data(), n_devices, ords.data()) != 0) {
+            fprintf(stderr, "sbv_create: NCCL initialisation failed: %s\n", e->err.c_str());
+            e->nccl_comms.clear();
+            sbv_destroy(e);
+            return SBV_ERR_NCCL;
+        }
+    }
     *out = e;
     return SBV_OK;
 }
 
 void sbv_destroy(sbv_engine *e) {
     if (!e) return;
+    for (void *c : e->nccl_comms) if (c && g_nccl.comm_destroy) g_nccl.comm_destroy(c);
     for (Dev &d : e->devs) {
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
@@ -245,12 +346,17 @@ int sbv_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *r, c
         if ((rc = h2d(e, d, d.d_dig, digest + sh.lo * digest_len, sh.n * digest_len, so, d.stream))) return rc;
         rc = launch_verify(e, d, curve, sh.n, d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, digest_len, d.d_ok, d.stream);
         if (rc) return rc;
-        CU(e, cudaMemcpyAsync(ok + sh.lo, d.d_ok, sh.n, cudaMemcpyDeviceToHost, d.stream));
+        if (G == 1) CU(e, cudaMemcpyAsync(ok + sh.lo, d.d_ok, sh.n, cudaMemcpyDeviceToHost, d.stream));
+    }
+    if (G > 1) {
+        int rc = gather_verdicts(e, n, ok);
+        if (rc) return rc;
     }
     for (int g = 0; g < G; g++) {
         CU(e, cudaSetDevice(e->devs[g].ordinal));
         CU(e, cudaStreamSynchronize(e->devs[g].stream));
     }
+    if (G > 1) unpack_verdicts(e, n, ok);
     return SBV_OK;
 }
 

@@ -45,6 +45,7 @@ struct sbv_engine {
     // NCCL (multi-device only; loaded lazily with dlopen so single-device users never touch it)
     void *nccl_lib = nullptr;
     std::vector<void *> nccl_comms;
+    std::vector<uint32_t> gather_words;  // host copy of the gathered verdict bitmask
     // key registry
     uint64_t verification_seq = 0;
     std::vector<uint64_t> key_ids;

@@ -45,7 +45,25 @@ def lib():
 
 
 def ncores() -> int:
-    return len(os.sched_getaffinity(0))
+    """Host cores this process may actually use: CPU affinity capped by the cgroup CPU quota (a
+    container that sees 128 CPUs but holds a 16-CPU quota gets throttled with 128 busy threads)."""
+    n = len(os.sched_getaffinity(0))
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            with open(path) as f:
+                parts = f.read().split()
+            if path.endswith("cpu.max"):
+                if parts[0] != "max":
+                    n = min(n, max(1, int(int(parts[0]) / int(parts[1]))))
+            else:
+                q = int(parts[0])
+                if q > 0:
+                    with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as g:
+                        n = min(n, max(1, q // int(g.read().split()[0])))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return n
 
 
 def verify_batch(curve, r, s, qx, qy, digest, nthreads=None) -> np.ndarray:

@@ -209,3 +209,16 @@ def test_quorum_counting_matches_reference_rules(eng):
     import consensus_b200 as sbv
     for n in range(1, 40):
         assert sbv.compute_quorum(n) == ref.compute_quorum(n)
+
+
+def test_multi_device_engine_nccl_gather():
+    """sbv_create with 2 devices: shards + ncclAllGather of the packed verdict mask (needs >= 2 GPUs)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import consensus_b200 as sbv
+    b = corpus.make_batch(P256, n=5003, K=16, seed=23, corrupt_rate=4)
+    want = oracle.verify_batch(P256, b["r"], b["s"], b["qx"], b["qy"], b["digest"])
+    with sbv.Engine(n_devices=2) as e2:
+        got = e2.verify_batch(P256, b["r"], b["s"], b["qx"], b["qy"], b["digest"])
+    assert (got == want).all()
