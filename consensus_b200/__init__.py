@@ -21,7 +21,8 @@ SYMBOLS = [
     "sbv_create", "sbv_destroy", "sbv_last_error", "sbv_device_count", "sbv_verify_batch",
     "sbv_verify_batch_device", "sbv_verify_batch_der", "sbv_sha256_batch", "sbv_hash_verify_batch",
     "sbv_verify_mixed", "sbv_quorum", "sbv_compute_quorum", "sbv_set_keys", "sbv_kernel_launches",
-    "sbv_probe_mad_rate", "sbv_profile_enable", "sbv_profile_read",
+    "sbv_probe_mad_rate", "sbv_profile_enable", "sbv_profile_read", "sbv_verify_registered",
+    "sbv_verify_registered_device",
 ]
 
 
@@ -142,6 +143,37 @@ class Engine:
         self._check(self._lib.sbv_verify_batch_device(self._h, C.c_int(device_index), C.c_uint8(curve), C.c_size_t(n), vp(d_r),
                                                       vp(d_s), vp(d_qx), vp(d_qy), vp(d_digest), C.c_uint8(dlen), vp(d_ok),
                                                       vp(stream)), "sbv_verify_batch_device")
+
+    def set_keys(self, curves, xy, ids=None, verification_seq=0):
+        """Registers keys (slot i = key i) and builds their comb tables.  xy: (n, 2, L) or (n, 96) bytes."""
+        curves = _u8(curves)
+        n = curves.size
+        xy = np.asarray(xy, dtype=np.uint8)
+        if xy.size != n * 96:  # fixed-width per-curve arrays -> 48-byte slots
+            L = xy.size // (2 * n)
+            slots = np.zeros((n, 2, 48), np.uint8)
+            slots[:, :, 48 - L:] = xy.reshape(n, 2, L)
+            xy = slots
+        xy = np.ascontiguousarray(xy.reshape(-1))
+        ids = np.ascontiguousarray(ids if ids is not None else np.arange(n), dtype=np.uint64)
+        self._check(self._lib.sbv_set_keys(self._h, C.c_uint64(verification_seq), C.c_size_t(n), ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                           _p8(curves), _p8(xy)), "sbv_set_keys")
+
+    def verify_registered(self, curve, key_slot, r, s, digest) -> np.ndarray:
+        key_slot = np.ascontiguousarray(key_slot, dtype=np.uint32)
+        r, s, digest = map(_u8, (r, s, digest))
+        n = key_slot.size
+        dlen = digest.size // n if n else 32
+        ok = np.zeros(n, np.uint8)
+        self._check(self._lib.sbv_verify_registered(self._h, C.c_uint8(curve), C.c_size_t(n), key_slot.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                    _p8(r), _p8(s), _p8(digest), C.c_uint8(dlen), _p8(ok)), "sbv_verify_registered")
+        return ok
+
+    def verify_registered_device(self, curve, n, d_slot, d_r, d_s, d_digest, dlen, d_ok, stream=0, device_index=0):
+        vp = C.c_void_p
+        self._check(self._lib.sbv_verify_registered_device(self._h, C.c_int(device_index), C.c_uint8(curve), C.c_size_t(n), vp(d_slot), vp(d_r),
+                                                           vp(d_s), vp(d_digest), C.c_uint8(dlen), vp(d_ok), vp(stream)),
+                    "sbv_verify_registered_device")
 
     def verify_batch_der(self, curve, sigs, sig_off, qxy, digest) -> np.ndarray:
         sigs = _u8(sigs if len(sigs) else np.zeros(1, np.uint8))

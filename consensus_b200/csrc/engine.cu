@@ -143,6 +143,12 @@ __global__ void k_mad_probe(uint32_t *out, uint32_t iters) {
 }
 
 
+}  // namespace
+int sbv_ensure_workspace(sbv_engine *e, Dev &d, size_t n) { return ensure_workspace(e, d, n); }
+int sbv_ensure_pinned(sbv_engine *e, Dev &d, size_t bytes) { return ensure_pinned(e, d, bytes); }
+int sbv_h2d(sbv_engine *e, Dev &d, void *dst, const void *src, size_t bytes, size_t &stage_off, cudaStream_t st) { return h2d(e, d, dst, src, bytes, stage_off, st); }
+namespace {
+
 // ---- NCCL, loaded with dlopen only by multi-device engines ----
 typedef int (*nccl_comm_init_all_t)(void **comms, int ndev, const int *devlist);
 typedef int (*nccl_comm_destroy_t)(void *comm);
@@ -287,6 +293,7 @@ void sbv_destroy(sbv_engine *e) {
         void *ptrs[] = {d.gtab[0], d.gtab[1], d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, d.d_ok, d.d_gidx, d.d_flags,
                         d.d_digits, d.d_msgs, d.d_off, d.d_scratch};
         for (void *p : ptrs) if (p) cudaFree(p);
+        sbv_keys_free(d);
         if (d.h_pin) cudaFreeHost(d.h_pin);
         if (d.stream) cudaStreamDestroy(d.stream);
     }

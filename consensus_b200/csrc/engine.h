@@ -30,6 +30,13 @@ struct Dev {
     // generic scratch (quorum, bitmask)
     uint8_t *d_scratch = nullptr;
     size_t scratch_cap = 0;
+    // registered keys (sbv_set_keys): per-curve comb tables, validity flags, slot -> table index
+    uint32_t *ktab[2] = {nullptr, nullptr};
+    uint8_t *keyflags[2] = {nullptr, nullptr};
+    int32_t *slot2local[2] = {nullptr, nullptr};
+    uint32_t n_slots = 0, n_local[2] = {0, 0};
+    uint32_t *d_slot = nullptr;
+    size_t slot_cap = 0;
     // profiling: event pairs around the prep / verify kernels (only when enabled)
     std::vector<cudaEvent_t> prof_events;  // triples: before prep, between, after verify
     size_t prof_used = 0;
@@ -82,4 +89,11 @@ int sbv_launch_p256_w3_b128(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r,
 int sbv_launch_p384_w3_b128(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                             const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
 int sbv_init_gtables(sbv_engine *e, Dev &d);  // gtable.cu
+int sbv_keys_build(sbv_engine *e, Dev &d);    // keyed.cu: (re)builds the per-key comb tables from the registry
+void sbv_keys_free(Dev &d);
+int sbv_launch_keyed(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint32_t *d_slot, const uint8_t *d_r, const uint8_t *d_s,
+                     const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
+int sbv_ensure_workspace(sbv_engine *e, Dev &d, size_t n);
+int sbv_ensure_pinned(sbv_engine *e, Dev &d, size_t bytes);
+int sbv_h2d(sbv_engine *e, Dev &d, void *dst, const void *src, size_t bytes, size_t &stage_off, cudaStream_t st);
 int sbv_ensure_scratch(sbv_engine *e, Dev &d, size_t bytes);

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restr
                                               uint8_t *__restrict__ gidx, int8_t *__restrict__ digits,
                                               uint8_t *__restrict__ flags) {
     constexpr int N = C::N;
-    constexpr int NWIN = Windows<32 * N, W>::COUNT;
+    constexpr int NWIN = W == 0 ? C::BYTES : Windows<32 * N, (W == 0 ? 1 : W)>::COUNT;
     const uint32_t T = gridDim.x * blockDim.x;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t sm[S][N];    // Montgomery form of s (or 1 when out of range)
@@ -144,20 +144,26 @@ __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restr
         // comb bytes of u1 (window i = byte i, little-endian)
 #pragma unroll
         for (int i = 0; i < C::BYTES; i++) gidx[(size_t)i * n + idx] = (uint8_t)(u1[i >> 2] >> (8 * (i & 3)));
+        if (W == 0) {  // registered-key path: u2 is consumed by a second comb, byte-wise
+#pragma unroll
+            for (int i = 0; i < C::BYTES; i++) digits[(size_t)i * n + idx] = (int8_t)(uint8_t)(u2[i >> 2] >> (8 * (i & 3)));
+            continue;
+        }
         // Booth digits of u2: window i looks at bits [W*i-1, W*i+W-1]
         for (int i = 0; i < NWIN; i++) {
-            int pos = W * i - 1;
+            constexpr int WW = W == 0 ? 1 : W;
+            int pos = WW * i - 1;
             uint32_t b;
             if (pos < 0) {
-                b = (u2[0] << 1) & ((2u << W) - 1);
+                b = (u2[0] << 1) & ((2u << WW) - 1);
             } else {
                 int wd = pos >> 5, sh = pos & 31;
                 uint32_t lo = wd <= N ? u2[wd] : 0u, hi = wd + 1 <= N ? u2[wd + 1] : 0u;
                 uint64_t v = ((uint64_t)hi << 32) | lo;
-                b = (uint32_t)(v >> sh) & ((2u << W) - 1);
+                b = (uint32_t)(v >> sh) & ((2u << WW) - 1);
             }
-            uint32_t sign = b >> W;
-            uint32_t d = sign ? (((2u << W) - 1) - b) : b;
+            uint32_t sign = b >> WW;
+            uint32_t d = sign ? (((2u << WW) - 1) - b) : b;
             d = (d + 1) >> 1;
             digits[(size_t)i * n + idx] = (int8_t)(sign ? -(int)d : (int)d);
         }
@@ -256,6 +262,143 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_verify(uint32_t n, const uint8_
     }
 #undef TAB
     // accept iff R != inf and R.x mod n == r  <=>  X == r*Z^2 or (r + n < p and X == (r+n)*Z^2)
+    bool match = false;
+    if (!mp_is_zero<N>(acc.Z)) {
+        uint32_t zz[N], r[N], rr[N], rm[N], lhs[N], pmn[N];
+        C::fsqr(zz, acc.Z);
+        load_be<N>(r, r_be + (size_t)idx * C::BYTES);
+        C::get_rr_p(rr);
+        C::fmul(rm, r, rr);
+        C::fmul(lhs, rm, zz);
+        match = mp_eq<N>(lhs, acc.X);
+        C::get_p_minus_n(pmn);
+        if (!match && mp_lt<N>(r, pmn)) {
+            uint32_t r2[N], nmod[N];
+            C::get_n(nmod);
+            mp_add<N>(r2, r, nmod);
+            C::fmul(rm, r2, rr);
+            C::fmul(lhs, rm, zz);
+            match = mp_eq<N>(lhs, acc.X);
+        }
+    }
+    ok_out[idx] = (good && match) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Registered-key path (sbv_set_keys): per-key affine comb table K[k][i][b] = b * 2^(8i) * Q_k, so
+// u2*Q is fixed-base as well — no doublings and no per-signature table.
+template <class C>
+__global__ void k_keytab_init(uint32_t n_keys, const uint8_t *__restrict__ keys_be, uint32_t *__restrict__ tab,
+                              uint8_t *__restrict__ keyflags) {
+    constexpr int N = C::N;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t per_key = (size_t)C::BYTES * 256;
+    if (t >= (size_t)n_keys * per_key) return;
+    const uint32_t key = (uint32_t)(t / per_key);
+    const int e = (int)(t % per_key), win = e >> 8, b = e & 255;
+    uint32_t *out = tab + t * 2 * N;
+    uint32_t x[N], y[N], pmod[N], rr[N];
+    load_be<N>(x, keys_be + (size_t)key * 2 * C::BYTES);
+    load_be<N>(y, keys_be + (size_t)key * 2 * C::BYTES + C::BYTES);
+    C::get_p(pmod);
+    C::get_rr_p(rr);
+    bool good = mp_lt<N>(x, pmod) && mp_lt<N>(y, pmod);
+    Jac<C> base;
+    C::fmul(base.X, x, rr);
+    C::fmul(base.Y, y, rr);
+    C::get_one(base.Z);
+    {
+        uint32_t lhs[N], rhs[N], tt[N], bb[N];
+        C::fsqr(lhs, base.Y);
+        C::fsqr(tt, base.X);
+        C::fmul(rhs, tt, base.X);
+        C::fsub(rhs, rhs, base.X); C::fsub(rhs, rhs, base.X); C::fsub(rhs, rhs, base.X);
+        C::get_b(bb);
+        C::fadd(rhs, rhs, bb);
+        good = good && mp_eq<N>(lhs, rhs);
+    }
+    if (e == 0) keyflags[key] = good ? 1 : 0;
+    if (b == 0 || !good) {
+        for (int i = 0; i < 2 * N; i++) out[i] = 0;
+        return;
+    }
+    for (int i = 0; i < 8 * win; i++) pt_double<C>(base);
+    Jac<C> acc;
+    C::get_one(acc.X); C::get_one(acc.Y);
+#pragma unroll
+    for (int i = 0; i < N; i++) acc.Z[i] = 0;
+    for (int bit = 7; bit >= 0; bit--) {
+        pt_double<C>(acc);
+        pt_add<C, false>(acc, base.X, base.Y, base.Z, false, !((b >> bit) & 1));
+    }
+    uint32_t zi[N], zi2[N], zi3[N], ox[N], oy[N];
+    f_inv<C>(zi, acc.Z);
+    C::fsqr(zi2, zi);
+    C::fmul(zi3, zi2, zi);
+    C::fmul(ox, acc.X, zi2);
+    C::fmul(oy, acc.Y, zi3);
+    for (int i = 0; i < N; i++) { out[i] = ox[i]; out[N + i] = oy[i]; }
+}
+
+template <class C>
+SBV_DEV void load_affine(uint32_t (&x)[C::N], uint32_t (&y)[C::N], const uint4 *src) {
+    constexpr int N = C::N;
+#pragma unroll
+    for (int i = 0; i < N / 4; i++) {
+        uint4 v = __ldg(src + i);
+        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+        uint4 u = __ldg(src + N / 4 + i);
+        y[4 * i] = u.x; y[4 * i + 1] = u.y; y[4 * i + 2] = u.z; y[4 * i + 3] = u.w;
+    }
+}
+
+template <class C, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_verify_keyed(uint32_t n, const uint32_t *__restrict__ slot, const int32_t *__restrict__ slot2local,
+                                                        uint32_t n_slots, const uint8_t *__restrict__ keyflags,
+                                                        const uint8_t *__restrict__ r_be, const uint8_t *__restrict__ gidx,
+                                                        const uint8_t *__restrict__ qidx, const uint8_t *__restrict__ flags,
+                                                        const uint4 *__restrict__ gtab, const uint4 *__restrict__ ktab,
+                                                        uint8_t *__restrict__ ok_out) {
+    constexpr int N = C::N;
+    constexpr int EU4 = 2 * N / 4;  // uint4 per table entry
+    const uint32_t idx = blockIdx.x * BLOCK + threadIdx.x;
+    if (idx >= n) return;
+    bool good = flags[idx] != 0;
+    const uint32_t sl = slot[idx];
+    int32_t local = sl < n_slots ? slot2local[sl] : -1;
+    good = good && local >= 0;
+    if (local < 0) local = 0;
+    good = good && keyflags[local] != 0;
+    const uint4 *kt = ktab + (size_t)local * C::BYTES * 256 * EU4;
+    uint32_t one[N];
+    C::get_one(one);
+    Jac<C> acc;
+    mp_copy<N>(acc.X, one);
+    mp_copy<N>(acc.Y, one);
+#pragma unroll
+    for (int i = 0; i < N; i++) acc.Z[i] = 0;
+    // software pipeline: the table entries of step w+1 are in flight while step w is added
+    uint32_t gx[N], gy[N], kx[N], ky[N];
+    uint32_t gb = gidx[idx], kb = qidx[idx];
+    load_affine<C>(gx, gy, gtab + (size_t)gb * EU4);
+    load_affine<C>(kx, ky, kt + (size_t)kb * EU4);
+#pragma unroll 1
+    for (int win = 0; win < C::BYTES; win++) {
+        uint32_t ngx[N], ngy[N], nkx[N], nky[N];
+        uint32_t ngb = 0, nkb = 0;
+        if (win + 1 < C::BYTES) {
+            ngb = gidx[(size_t)(win + 1) * n + idx];
+            nkb = qidx[(size_t)(win + 1) * n + idx];
+            load_affine<C>(ngx, ngy, gtab + ((size_t)(win + 1) * 256 + ngb) * EU4);
+            load_affine<C>(nkx, nky, kt + ((size_t)(win + 1) * 256 + nkb) * EU4);
+        }
+        pt_add<C, true>(acc, gx, gy, one, false, gb == 0);
+        pt_add<C, true>(acc, kx, ky, one, false, kb == 0);
+        if (win + 1 < C::BYTES) {
+            mp_copy<N>(gx, ngx); mp_copy<N>(gy, ngy); mp_copy<N>(kx, nkx); mp_copy<N>(ky, nky);
+            gb = ngb; kb = nkb;
+        }
+    }
     bool match = false;
     if (!mp_is_zero<N>(acc.Z)) {
         uint32_t zz[N], r[N], rr[N], rm[N], lhs[N], pmn[N];

@@ -106,9 +106,23 @@ int sbv_quorum(sbv_engine *e, size_t n_votes, const uint32_t *instance, const ui
 /* computeQuorum(n) -> (q, f), internal/bft/util.go:183-187. */
 void sbv_compute_quorum(uint64_t n, uint32_t *q, uint32_t *f);
 
-/* Consenter key registry (ID -> public key) for the host-side Verifier mirror. */
+/* Consenter key registry.  Keys are configuration in the reference: they change only with a
+ * reconfiguration, i.e. a new VerificationSequence (dependencies.go:65-66).  sbv_set_keys replaces
+ * the registry and precomputes, on every device, a fixed-base comb table per key
+ * (32*256 affine points = 512 KiB per P-256 key); slot i of the registry is key i of this call.
+ * xy = n * 96 bytes: X and Y in 48-byte slots (P-256 values right-aligned). */
 int sbv_set_keys(sbv_engine *e, uint64_t verification_seq, size_t n, const uint64_t *ids, const uint8_t *curve,
-                 const uint8_t *xy /* n * 96 bytes, 48-byte slots */);
+                 const uint8_t *xy);
+
+/* ECDSA verify against REGISTERED keys: key_slot[i] indexes the registry of sbv_set_keys.  Same accept
+ * set as sbv_verify_batch; an unknown slot, a slot of another curve or an invalid registered key
+ * rejects.  Both scalar multiplications are fixed-base (no doublings), which is ~5x less work than
+ * the keys-per-item entry point. */
+int sbv_verify_registered(sbv_engine *e, uint8_t curve, size_t n, const uint32_t *key_slot, const uint8_t *r,
+                          const uint8_t *s, const uint8_t *digest, uint8_t digest_len, uint8_t *ok);
+int sbv_verify_registered_device(sbv_engine *e, int device_index, uint8_t curve, size_t n, const uint32_t *d_key_slot,
+                                 const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_digest, uint8_t digest_len,
+                                 uint8_t *d_ok, void *cuda_stream);
 
 /* Introspection for benchmarks: number of kernel launches issued by this engine so far. */
 uint64_t sbv_kernel_launches(const sbv_engine *e);

@@ -222,3 +222,50 @@ def test_multi_device_engine_nccl_gather():
     with sbv.Engine(n_devices=2) as e2:
         got = e2.verify_batch(P256, b["r"], b["s"], b["qx"], b["qy"], b["digest"])
     assert (got == want).all()
+
+
+@pytest.mark.parametrize("curve", [P256, P384])
+def test_registered_key_path_bit_exact(eng, curve):
+    """sbv_set_keys + sbv_verify_registered (fixed-base comb per key) must give the oracle's verdicts,
+    including for an invalid registered key, a slot of the other curve and an unknown slot."""
+    L = 32 if curve == P256 else 48
+    n, K = 3000, 12
+    b = corpus.make_batch(curve, n=n, K=K, seed=61 + curve, corrupt_rate=0)
+    keys = b["keys"].reshape(K, 2, L).copy()
+    other = corpus.make_keys(1 - curve, 2, seed=5)[1].reshape(2, 2, 32 if curve == P384 else 48)
+    slots_xy = np.zeros((K + 3, 2, 48), np.uint8)
+    slots_xy[:K, :, 48 - L:] = keys
+    slots_xy[K, :, 48 - L:] = keys[0]; slots_xy[K, 1, 47] ^= 1            # slot K: off-curve key
+    Lo = other.shape[2]
+    slots_xy[K + 1, :, 48 - Lo:] = other[0]                                # slot K+1: key of the other curve
+    slots_xy[K + 2, :, 48 - L:] = keys[1]                                  # slot K+2: valid duplicate of key 1
+    curves = np.full(K + 3, curve, np.uint8); curves[K + 1] = 1 - curve
+    eng.set_keys(curves, slots_xy, verification_seq=7)
+    slot = b["key_idx"].astype(np.uint32).copy()
+    r, s, dig = b["r"].copy(), b["s"].copy(), b["digest"].copy()
+    rng = np.random.default_rng(3)
+    qx, qy = b["qx"].copy(), b["qy"].copy()
+    for i in range(n):
+        m = i % 16
+        if m == 1: r[i, rng.integers(L)] ^= 1 << rng.integers(8)
+        elif m == 2: s[i, rng.integers(L)] ^= 1 << rng.integers(8)
+        elif m == 3: dig[i, rng.integers(32)] ^= 1 << rng.integers(8)
+        elif m == 4:                                   # signed by key k, verified against another registered key
+            slot[i] = (slot[i] + 1) % K; qx[i] = keys[slot[i], 0]; qy[i] = keys[slot[i], 1]
+        elif m == 5: slot[i] = K; qy[i] = slots_xy[K, 1, 48 - L:]      # invalid key
+        elif m == 6: slot[i] = K + 1                                      # other-curve slot  -> reject
+        elif m == 7: slot[i] = K + 3 + 11                                 # unknown slot      -> reject
+        elif m == 8: r[i] = 0
+        elif m == 9 and slot[i] == 1: slot[i] = K + 2                     # duplicate registration of the same key
+    want = oracle.verify_batch(curve, r, s, qx, qy, dig)
+    want[np.isin(np.arange(n) % 16, [6, 7])] = 0
+    got = eng.verify_registered(curve, slot, r, s, dig)
+    bad = np.nonzero(want != got)[0]
+    assert bad.size == 0, (bad[:10], (bad[:10] % 16))
+    assert 0 < want.sum() < n
+    # agrees with the keys-per-item entry point wherever the slot is a valid key of this curve
+    sel = ~np.isin(np.arange(n) % 16, [5, 6, 7])
+    generic = eng.verify_batch(curve, r[sel], s[sel], qx[sel], qy[sel], dig[sel])
+    assert (generic == got[sel]).all()
+    eng.set_keys(np.zeros(0, np.uint8), np.zeros((0, 96), np.uint8))      # empty registry: everything rejects
+    assert eng.verify_registered(curve, slot[:50], r[:50], s[:50], dig[:50]).sum() == 0

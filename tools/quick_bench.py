@@ -14,7 +14,7 @@ dev = torch.device("cuda:0")
 t = {k: torch.from_numpy(b[k]).to(dev) for k in ("r", "s", "qx", "qy", "digest")}
 ok = torch.zeros(n, dtype=torch.uint8, device=dev)
 res = {}
-for w, blk in [(3, 64), (3, 128), (4, 128)]:
+for w, blk in [(3, 64)]:
     os.environ["SBV_P256_W"] = str(w); os.environ["SBV_P256_BLOCK"] = str(blk)
     e = sbv.Engine(n_devices=1)
     if "mad" not in res:
@@ -34,4 +34,28 @@ for w, blk in [(3, 64), (3, 128), (4, 128)]:
     t0 = time.time(); got = e.verify_batch(P256, b["r"], b["s"], b["qx"], b["qy"], b["digest"]); t1 = time.time()
     res[f"W{w}_B{blk}"]["e2e_pageable_ms"] = (t1 - t0) * 1e3
     e.close()
+e = sbv.Engine(n_devices=1)
+t0 = time.time(); e.set_keys(np.zeros(1024, np.uint8), b["keys"].reshape(1024, 2, 32)); res["set_keys_1024_s"] = time.time() - t0
+slot = torch.from_numpy(b["key_idx"].astype(np.int32)).to(dev)
+runk = lambda: e.verify_registered_device(P256, n, slot.data_ptr(), t["r"].data_ptr(), t["s"].data_ptr(), t["digest"].data_ptr(), 32, ok.data_ptr(), stream=st)
+for _ in range(3): runk()
+torch.cuda.synchronize()
+want_k = oracle.verify_batch(P256, b["r"], b["s"], np.ascontiguousarray(b["keys"][b["key_idx"], :32]), np.ascontiguousarray(b["keys"][b["key_idx"], 32:]), b["digest"])
+assert (ok.cpu().numpy() == want_k).all(), "parity keyed"
+a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(10): runk()
+c.record(); torch.cuda.synchronize()
+ms = a.elapsed_time(c) / 10
+res["registered_1024keys"] = {"ms": ms, "Mverif_s": n / ms / 1e3}
+t0 = time.time(); got = e.verify_registered(P256, b["key_idx"], b["r"], b["s"], b["digest"]); res["registered_1024keys"]["e2e_pageable_ms"] = (time.time() - t0) * 1e3
+e.set_keys(np.zeros(16, np.uint8), b["keys"].reshape(1024, 2, 32)[:16])
+slot16 = torch.from_numpy((b["key_idx"] % 16).astype(np.int32)).to(dev)
+runk = lambda: e.verify_registered_device(P256, n, slot16.data_ptr(), t["r"].data_ptr(), t["s"].data_ptr(), t["digest"].data_ptr(), 32, ok.data_ptr(), stream=st)
+for _ in range(3): runk()
+a.record()
+for _ in range(10): runk()
+c.record(); torch.cuda.synchronize()
+res["registered_16keys"] = {"ms": a.elapsed_time(c) / 10, "Mverif_s": n / (a.elapsed_time(c) / 10) / 1e3}
+e.close()
 print(json.dumps(res, indent=1))
