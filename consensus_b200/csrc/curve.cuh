@@ -21,6 +21,8 @@ static __device__ __noinline__ Fe8 p256_fsqr_call(Fe8 a);
 struct P256 {
     static constexpr int N = 8;
     static constexpr int BYTES = 32;
+    static constexpr int GW = 16;              // fixed-base comb window of G: 16 windows x 65536 entries (64 MB, L2-resident)
+    static constexpr int GWINS = 256 / GW;
     static constexpr uint32_t NINV = SBV_P256_NINV;
 
     SBV_DEV static void get_p(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_P; mp_copy<8>(r, c); }
@@ -135,6 +137,8 @@ static __device__ __noinline__ Fe8 p256_fsqr_call(Fe8 a) {
 struct P384 {
     static constexpr int N = 12;
     static constexpr int BYTES = 48;
+    static constexpr int GW = 8;               // 48 windows x 256 entries (a 16-bit comb would be 151 MB)
+    static constexpr int GWINS = 384 / GW;
 
     SBV_DEV static void get_p(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_P; mp_copy<12>(r, c); }
     SBV_DEV static void get_n(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_N; mp_copy<12>(r, c); }

@@ -32,7 +32,9 @@ int ensure_workspace(sbv_engine *e, Dev &d, size_t n) {
     if (n <= d.cap) return 0;
     size_t cap = n + n / 8 + 1024;
     CU(e, cudaSetDevice(d.ordinal));
-    uint8_t **ptrs[] = {&d.d_r, &d.d_s, &d.d_qx, &d.d_qy, &d.d_dig, &d.d_ok, &d.d_gidx, &d.d_flags};
+    uint8_t **ptrs[] = {&d.d_r, &d.d_s, &d.d_qx, &d.d_qy, &d.d_dig, &d.d_ok, &d.d_flags};
+    if (d.d_gidx) cudaFree(d.d_gidx);
+    d.d_gidx = nullptr;
     for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
     if (d.d_digits) cudaFree(d.d_digits);
     CU(e, cudaMalloc(&d.d_r, cap * 48));
@@ -41,7 +43,7 @@ int ensure_workspace(sbv_engine *e, Dev &d, size_t n) {
     CU(e, cudaMalloc(&d.d_qy, cap * 48));
     CU(e, cudaMalloc(&d.d_dig, cap * 64));
     CU(e, cudaMalloc(&d.d_ok, cap));
-    CU(e, cudaMalloc(&d.d_gidx, cap * 48));
+    CU(e, cudaMalloc(&d.d_gidx, cap * 48 * sizeof(uint16_t)));
     CU(e, cudaMalloc(&d.d_flags, cap));
     CU(e, cudaMalloc(&d.d_digits, cap * 132));
     d.cap = cap;
@@ -119,8 +121,6 @@ int launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t 
                   cudaStream_t st) {
     if (n == 0) return 0;
     if (curve == SBV_P256) {
-        if (e->p256_w == 4) return sbv_launch_p256_w4_b128(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
-        if (e->p256_block == 128) return sbv_launch_p256_w3_b128(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
         return sbv_launch_p256_w3_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
     }
     return sbv_launch_p384_w3_b128(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
@@ -254,8 +254,6 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count < n_devices) return SBV_ERR_CUDA;
     sbv_engine *e = new sbv_engine();
-    e->p256_w = env_int("SBV_P256_W", 3);
-    e->p256_block = env_int("SBV_P256_BLOCK", 64);
     e->devs.resize(n_devices);
     for (int g = 0; g < n_devices; g++) {
         Dev &d = e->devs[g];

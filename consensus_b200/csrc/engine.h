@@ -18,7 +18,8 @@ struct Dev {
     // per-batch workspace (device)
     size_t cap = 0;
     uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr, *d_qy = nullptr, *d_dig = nullptr, *d_ok = nullptr;
-    uint8_t *d_gidx = nullptr, *d_flags = nullptr;
+    uint16_t *d_gidx = nullptr;
+    uint8_t *d_flags = nullptr;
     int8_t *d_digits = nullptr;
     // message workspace
     size_t msg_cap = 0, off_cap = 0;
@@ -80,12 +81,8 @@ inline int sbv_fail(sbv_engine *e, int code, const char *fmt, ...) {
     } while (0)
 
 // per-(curve, window, block) kernel launchers — one translation unit each (inst_*.cu)
-int sbv_launch_p256_w4_b128(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
-                            const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
 int sbv_launch_p256_w3_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                            const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
-int sbv_launch_p256_w3_b128(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
-                            const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
 int sbv_launch_p384_w3_b128(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                             const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
 int sbv_init_gtables(sbv_engine *e, Dev &d);  // gtable.cu

@@ -1,6 +1,6 @@
 // kernels.cuh — sm_100a kernels of the sbv hot path (ECDSA verify over NIST prime curves).
 //
-//   k_gtable_init  one-time: affine fixed-base comb table  T[i][b] = b * 2^(8i) * G  (Montgomery form)
+//   k_gtable_init  one-time: affine fixed-base comb table  T[i][b] = b * 2^(GW*i) * G  (Montgomery form; GW = 16 for P-256)
 //   k_prep         per batch: range checks, batched inversion of s mod n (Montgomery's trick, S items
 //                  per thread), u1 = e/s, u2 = r/s, comb bytes of u1 and Booth digits of u2 written
 //                  window-major so the verify kernel reads them coalesced
@@ -23,13 +23,25 @@ struct Windows {
     static constexpr int ENTRIES = 1 << (W - 1);          // table holds 1..2^(W-1) times Q
 };
 
+template <class C>
+SBV_DEV void load_affine(uint32_t (&x)[C::N], uint32_t (&y)[C::N], const uint4 *src) {
+    constexpr int N = C::N;
+#pragma unroll
+    for (int i = 0; i < N / 4; i++) {
+        uint4 v = __ldg(src + i);
+        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+        uint4 u = __ldg(src + N / 4 + i);
+        y[4 * i] = u.x; y[4 * i + 1] = u.y; y[4 * i + 2] = u.z; y[4 * i + 3] = u.w;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 template <class C>
 __global__ void k_gtable_init(uint32_t *__restrict__ gtab) {
     constexpr int N = C::N;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= C::BYTES * 256) return;
-    const int win = t >> 8, b = t & 255;
+    if (t >= C::GWINS << C::GW) return;
+    const int win = t >> C::GW, b = t & ((1 << C::GW) - 1);
     uint32_t *out = gtab + (size_t)t * 2 * N;
     if (b == 0) {
         for (int i = 0; i < 2 * N; i++) out[i] = 0;
@@ -37,12 +49,12 @@ __global__ void k_gtable_init(uint32_t *__restrict__ gtab) {
     }
     Jac<C> base;
     C::get_gx(base.X); C::get_gy(base.Y); C::get_one(base.Z);
-    for (int i = 0; i < 8 * win; i++) pt_double<C>(base);
+    for (int i = 0; i < C::GW * win; i++) pt_double<C>(base);
     Jac<C> acc;
     C::get_one(acc.X); C::get_one(acc.Y);
 #pragma unroll
     for (int i = 0; i < N; i++) acc.Z[i] = 0;
-    for (int bit = 7; bit >= 0; bit--) {
+    for (int bit = C::GW - 1; bit >= 0; bit--) {
         pt_double<C>(acc);
         pt_add<C, false>(acc, base.X, base.Y, base.Z, false, !((b >> bit) & 1));
     }
@@ -78,7 +90,7 @@ SBV_DEV void load_digest(uint32_t (&e)[C::N], const uint8_t *d, uint32_t dlen) {
 template <class C, int W, int S>
 __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restrict__ r_be, const uint8_t *__restrict__ s_be,
                                               const uint8_t *__restrict__ dig_be, uint32_t dlen,
-                                              uint8_t *__restrict__ gidx, int8_t *__restrict__ digits,
+                                              uint16_t *__restrict__ gidx, int8_t *__restrict__ digits,
                                               uint8_t *__restrict__ flags) {
     constexpr int N = C::N;
     constexpr int NWIN = W == 0 ? C::BYTES : Windows<32 * N, (W == 0 ? 1 : W)>::COUNT;
@@ -141,9 +153,9 @@ __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restr
             for (int i = 0; i < N; i++) u2[i] = tmp[i];
             u2[N] = 0;
         }
-        // comb bytes of u1 (window i = byte i, little-endian)
+        // comb digits of u1 (GW bits each, little-endian)
 #pragma unroll
-        for (int i = 0; i < C::BYTES; i++) gidx[(size_t)i * n + idx] = (uint8_t)(u1[i >> 2] >> (8 * (i & 3)));
+        for (int i = 0; i < C::GWINS; i++) gidx[(size_t)i * n + idx] = (uint16_t)((u1[(i * C::GW) >> 5] >> ((i * C::GW) & 31)) & ((1u << C::GW) - 1));
         if (W == 0) {  // registered-key path: u2 is consumed by a second comb, byte-wise
 #pragma unroll
             for (int i = 0; i < C::BYTES; i++) digits[(size_t)i * n + idx] = (int8_t)(uint8_t)(u2[i >> 2] >> (8 * (i & 3)));
@@ -173,7 +185,7 @@ __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restr
 // ------------------------------------------------------------------------------------------------
 template <class C, int W, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_verify(uint32_t n, const uint8_t *__restrict__ qx_be, const uint8_t *__restrict__ qy_be,
-                                                  const uint8_t *__restrict__ r_be, const uint8_t *__restrict__ gidx,
+                                                  const uint8_t *__restrict__ r_be, const uint16_t *__restrict__ gidx,
                                                   const int8_t *__restrict__ digits, const uint8_t *__restrict__ flags,
                                                   const uint4 *__restrict__ gtab, uint8_t *__restrict__ ok_out) {
     constexpr int N = C::N;
@@ -245,20 +257,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_verify(uint32_t n, const uint8_
             pt_add<C, false>(acc, x2, y2, z2, neg, skip);
         }
     }
-    // u1*G from the fixed-base comb: BYTES complete points, added after the last doubling
+    // u1*G from the fixed-base comb: GWINS complete points, added after the last doubling.  The next
+    // entry (a random 64 B gather from the L2-resident table) is in flight while the current one is added.
+    {
+        constexpr int EU4 = 2 * N / 4;
+        uint32_t gx[N], gy[N];
+        uint32_t gb = gidx[idx];
+        load_affine<C>(gx, gy, gtab + (size_t)gb * EU4);
 #pragma unroll 1
-    for (int win = 0; win < C::BYTES; win++) {
-        uint32_t b = gidx[(size_t)win * n + idx];
-        const uint4 *src = gtab + ((size_t)win * 256 + b) * (2 * N / 4);
-        uint32_t x2[N], y2[N];
-#pragma unroll
-        for (int i = 0; i < N / 4; i++) {
-            uint4 v = __ldg(src + i);
-            x2[4 * i] = v.x; x2[4 * i + 1] = v.y; x2[4 * i + 2] = v.z; x2[4 * i + 3] = v.w;
-            uint4 u = __ldg(src + N / 4 + i);
-            y2[4 * i] = u.x; y2[4 * i + 1] = u.y; y2[4 * i + 2] = u.z; y2[4 * i + 3] = u.w;
+        for (int win = 0; win < C::GWINS; win++) {
+            uint32_t ngx[N], ngy[N];
+            uint32_t ngb = 0;
+            if (win + 1 < C::GWINS) {
+                ngb = gidx[(size_t)(win + 1) * n + idx];
+                load_affine<C>(ngx, ngy, gtab + (((size_t)(win + 1) << C::GW) + ngb) * EU4);
+            }
+            pt_add<C, true>(acc, gx, gy, one, false, gb == 0);
+            if (win + 1 < C::GWINS) { mp_copy<N>(gx, ngx); mp_copy<N>(gy, ngy); gb = ngb; }
         }
-        pt_add<C, true>(acc, x2, y2, one, false, b == 0);
     }
 #undef TAB
     // accept iff R != inf and R.x mod n == r  <=>  X == r*Z^2 or (r + n < p and X == (r+n)*Z^2)
@@ -340,22 +356,10 @@ __global__ void k_keytab_init(uint32_t n_keys, const uint8_t *__restrict__ keys_
     for (int i = 0; i < N; i++) { out[i] = ox[i]; out[N + i] = oy[i]; }
 }
 
-template <class C>
-SBV_DEV void load_affine(uint32_t (&x)[C::N], uint32_t (&y)[C::N], const uint4 *src) {
-    constexpr int N = C::N;
-#pragma unroll
-    for (int i = 0; i < N / 4; i++) {
-        uint4 v = __ldg(src + i);
-        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
-        uint4 u = __ldg(src + N / 4 + i);
-        y[4 * i] = u.x; y[4 * i + 1] = u.y; y[4 * i + 2] = u.z; y[4 * i + 3] = u.w;
-    }
-}
-
 template <class C, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_verify_keyed(uint32_t n, const uint32_t *__restrict__ slot, const int32_t *__restrict__ slot2local,
                                                         uint32_t n_slots, const uint8_t *__restrict__ keyflags,
-                                                        const uint8_t *__restrict__ r_be, const uint8_t *__restrict__ gidx,
+                                                        const uint8_t *__restrict__ r_be, const uint16_t *__restrict__ gidx,
                                                         const uint8_t *__restrict__ qidx, const uint8_t *__restrict__ flags,
                                                         const uint4 *__restrict__ gtab, const uint4 *__restrict__ ktab,
                                                         uint8_t *__restrict__ ok_out) {
@@ -377,26 +381,35 @@ __global__ void __launch_bounds__(BLOCK) k_verify_keyed(uint32_t n, const uint32
     mp_copy<N>(acc.Y, one);
 #pragma unroll
     for (int i = 0; i < N; i++) acc.Z[i] = 0;
-    // software pipeline: the table entries of step w+1 are in flight while step w is added
-    uint32_t gx[N], gy[N], kx[N], ky[N];
-    uint32_t gb = gidx[idx], kb = qidx[idx];
-    load_affine<C>(gx, gy, gtab + (size_t)gb * EU4);
+    // software pipeline: the table entries of the next step are in flight while the current one is added
+    uint32_t kx[N], ky[N];
+    uint32_t kb = qidx[idx];
     load_affine<C>(kx, ky, kt + (size_t)kb * EU4);
 #pragma unroll 1
-    for (int win = 0; win < C::BYTES; win++) {
-        uint32_t ngx[N], ngy[N], nkx[N], nky[N];
-        uint32_t ngb = 0, nkb = 0;
+    for (int win = 0; win < C::BYTES; win++) {  // u2 * Q_k : 8-bit comb of the registered key
+        uint32_t nkx[N], nky[N];
+        uint32_t nkb = 0;
         if (win + 1 < C::BYTES) {
-            ngb = gidx[(size_t)(win + 1) * n + idx];
             nkb = qidx[(size_t)(win + 1) * n + idx];
-            load_affine<C>(ngx, ngy, gtab + ((size_t)(win + 1) * 256 + ngb) * EU4);
             load_affine<C>(nkx, nky, kt + ((size_t)(win + 1) * 256 + nkb) * EU4);
         }
-        pt_add<C, true>(acc, gx, gy, one, false, gb == 0);
         pt_add<C, true>(acc, kx, ky, one, false, kb == 0);
-        if (win + 1 < C::BYTES) {
-            mp_copy<N>(gx, ngx); mp_copy<N>(gy, ngy); mp_copy<N>(kx, nkx); mp_copy<N>(ky, nky);
-            gb = ngb; kb = nkb;
+        if (win + 1 < C::BYTES) { mp_copy<N>(kx, nkx); mp_copy<N>(ky, nky); kb = nkb; }
+    }
+    {
+        uint32_t gx[N], gy[N];
+        uint32_t gb = gidx[idx];
+        load_affine<C>(gx, gy, gtab + (size_t)gb * EU4);
+#pragma unroll 1
+        for (int win = 0; win < C::GWINS; win++) {  // u1 * G : GW-bit comb
+            uint32_t ngx[N], ngy[N];
+            uint32_t ngb = 0;
+            if (win + 1 < C::GWINS) {
+                ngb = gidx[(size_t)(win + 1) * n + idx];
+                load_affine<C>(ngx, ngy, gtab + (((size_t)(win + 1) << C::GW) + ngb) * EU4);
+            }
+            pt_add<C, true>(acc, gx, gy, one, false, gb == 0);
+            if (win + 1 < C::GWINS) { mp_copy<N>(gx, ngx); mp_copy<N>(gy, ngy); gb = ngb; }
         }
     }
     bool match = false;

@@ -15,7 +15,6 @@ t = {k: torch.from_numpy(b[k]).to(dev) for k in ("r", "s", "qx", "qy", "digest")
 ok = torch.zeros(n, dtype=torch.uint8, device=dev)
 res = {}
 for w, blk in [(3, 64)]:
-    os.environ["SBV_P256_W"] = str(w); os.environ["SBV_P256_BLOCK"] = str(blk)
     e = sbv.Engine(n_devices=1)
     if "mad" not in res:
         res["mad_rate_TMAC_s"] = e.probe_mad_rate() / 1e12
