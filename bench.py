@@ -322,9 +322,18 @@ def main():
         line["cpu_baseline"] = {"value": BATCH * reps / tot, "unit": "verifies/s", "cores": cores, "kind": "port",
                                 "sample": f"{reps} x the full 65,536-signature batch; OpenSSL 3.0 ECDSA_do_verify on pre-built keys "
                                           "(stand-in for Go crypto/ecdsa: no Go toolchain)"}
+    eng.close()
+    if rank == 0 and world == 1:
+        # consensus tx/s at n=4 (BASELINE configs[0]): in-process normal-path simulator, 1,000 txs,
+        # RequestBatchMaxCount = 100; accept-all (= stock naive_chain) vs per-call CPU verifier vs GPU verifier
+        sim = os.path.join(ROOT, "consensus_b200", "host", "sim")
+        try:
+            out = subprocess.run([sim, "1000", "100", "1"], capture_output=True, text=True, timeout=300)
+            line["consensus_n4"] = json.loads(out.stdout.strip().splitlines()[-1])
+        except Exception as ex:
+            line["consensus_n4"] = {"error": str(ex)}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

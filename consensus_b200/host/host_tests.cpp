@@ -3,11 +3,6 @@
 // real ECDSA signatures (OpenSSL is used HERE ONLY, as the test's signer).
 //
 // Each test names the reference test it mirrors (/root/reference/internal/bft/*_test.go).
-#include <openssl/bn.h>
-#include <openssl/ec.h>
-#include <openssl/ecdsa.h>
-#include <openssl/obj_mac.h>
-
 #include <array>
 #include <atomic>
 #include <cstdio>
@@ -224,32 +219,7 @@ static void TestAggregatorCoalesces() {
 }
 
 // ================================================================================================ GPU part
-struct TestKey { EC_KEY *k; uint8_t xy[64]; };
-static TestKey makeKey() {
-    TestKey t;
-    t.k = EC_KEY_new_by_curve_name(NID_X9_62_prime256v1);
-    EC_KEY_generate_key(t.k);
-    BIGNUM *x = BN_new(), *y = BN_new();
-    EC_POINT_get_affine_coordinates(EC_KEY_get0_group(t.k), EC_KEY_get0_public_key(t.k), x, y, nullptr);
-    BN_bn2binpad(x, t.xy, 32); BN_bn2binpad(y, t.xy + 32, 32);
-    BN_free(x); BN_free(y);
-    return t;
-}
-static Bytes signDer(const TestKey &k, const Bytes &msg) {
-    Bytes dig = sha256(msg);
-    unsigned int len = ECDSA_size(k.k);
-    Bytes sig(len);
-    ECDSA_sign(0, dig.data(), 32, sig.data(), &len, k.k);
-    sig.resize(len);
-    return sig;
-}
-// Signer.SignProposal under the INTEGRATION.md convention: Msg = digest(prop) || aux
-static Signature signProposal(uint64_t id, const TestKey &k, const Proposal &p, const Bytes &aux) {
-    Signature s; s.ID = id;
-    s.Msg = p.DigestRaw(); s.Msg.insert(s.Msg.end(), aux.begin(), aux.end());
-    s.Value = signDer(k, s.Msg);
-    return s;
-}
+#include "test_signer.hpp"
 
 static void TestGpuVerifierEndToEnd() {
     GpuVerifier v({0});
