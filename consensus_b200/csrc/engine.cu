@@ -32,20 +32,27 @@ int ensure_workspace(sbv_engine *e, Dev &d, size_t n) {
     if (n <= d.cap) return 0;
     size_t cap = n + n / 8 + 1024;
     CU(e, cudaSetDevice(d.ordinal));
-    uint8_t **ptrs[] = {&d.d_r, &d.d_s, &d.d_qx, &d.d_qy, &d.d_dig, &d.d_ok, &d.d_flags};
-    if (d.d_gidx) cudaFree(d.d_gidx);
-    d.d_gidx = nullptr;
+    uint8_t **ptrs[] = {&d.d_r, &d.d_s, &d.d_qx, &d.d_qy, &d.d_dig, &d.d_ok};
+    CU(e, cudaDeviceSynchronize());  // nothing may still be using the old scratch
     for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
-    if (d.d_digits) cudaFree(d.d_digits);
+    for (auto &w : d.ws) {
+        if (w.gidx) cudaFree(w.gidx);
+        if (w.digits) cudaFree(w.digits);
+        if (w.flags) cudaFree(w.flags);
+        w.gidx = nullptr; w.digits = nullptr; w.flags = nullptr; w.used = false;
+        if (!w.done) CU(e, cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
+    }
     CU(e, cudaMalloc(&d.d_r, cap * 48));
     CU(e, cudaMalloc(&d.d_s, cap * 48));
     CU(e, cudaMalloc(&d.d_qx, cap * 48));
     CU(e, cudaMalloc(&d.d_qy, cap * 48));
     CU(e, cudaMalloc(&d.d_dig, cap * 64));
     CU(e, cudaMalloc(&d.d_ok, cap));
-    CU(e, cudaMalloc(&d.d_gidx, cap * 48 * sizeof(uint16_t)));
-    CU(e, cudaMalloc(&d.d_flags, cap));
-    CU(e, cudaMalloc(&d.d_digits, cap * 132));
+    for (auto &w : d.ws) {
+        CU(e, cudaMalloc(&w.gidx, cap * 48 * sizeof(uint16_t)));
+        CU(e, cudaMalloc(&w.flags, cap));
+        CU(e, cudaMalloc(&w.digits, cap * 132));
+    }
     d.cap = cap;
     return 0;
 }
@@ -145,6 +152,13 @@ __global__ void k_mad_probe(uint32_t *out, uint32_t iters) {
 
 }  // namespace
 int sbv_ensure_workspace(sbv_engine *e, Dev &d, size_t n) { return ensure_workspace(e, d, n); }
+int sbv_take_scratch(sbv_engine *e, Dev &d, cudaStream_t st, Dev::Scratch **out) {
+    Dev::Scratch &w = d.ws[d.ws_next++ & 1];
+    if (w.used) CU(e, cudaStreamWaitEvent(st, w.done, 0));
+    w.used = true;
+    *out = &w;
+    return 0;
+}
 int sbv_ensure_pinned(sbv_engine *e, Dev &d, size_t bytes) { return ensure_pinned(e, d, bytes); }
 int sbv_h2d(sbv_engine *e, Dev &d, void *dst, const void *src, size_t bytes, size_t &stage_off, cudaStream_t st) { return h2d(e, d, dst, src, bytes, stage_off, st); }
 namespace {
@@ -288,8 +302,9 @@ void sbv_destroy(sbv_engine *e) {
     for (Dev &d : e->devs) {
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        void *ptrs[] = {d.gtab[0], d.gtab[1], d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, d.d_ok, d.d_gidx, d.d_flags,
-                        d.d_digits, d.d_msgs, d.d_off, d.d_scratch};
+        void *ptrs[] = {d.gtab[0], d.gtab[1], d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, d.d_ok, d.ws[0].gidx, d.ws[0].flags, d.ws[0].digits,
+                        d.ws[1].gidx, d.ws[1].flags, d.ws[1].digits, d.d_msgs, d.d_off, d.d_scratch};
+        for (auto &w : d.ws) if (w.done) cudaEventDestroy(w.done);
         for (void *p : ptrs) if (p) cudaFree(p);
         sbv_keys_free(d);
         if (d.h_pin) cudaFreeHost(d.h_pin);

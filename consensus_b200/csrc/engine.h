@@ -18,9 +18,16 @@ struct Dev {
     // per-batch workspace (device)
     size_t cap = 0;
     uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr, *d_qy = nullptr, *d_dig = nullptr, *d_ok = nullptr;
-    uint16_t *d_gidx = nullptr;
-    uint8_t *d_flags = nullptr;
-    int8_t *d_digits = nullptr;
+    // k_prep -> k_verify scratch, double-buffered so that launches on different streams may overlap:
+    // a launch takes the next set and first waits for the event of that set's previous user.
+    struct Scratch {
+        uint16_t *gidx = nullptr;
+        int8_t *digits = nullptr;
+        uint8_t *flags = nullptr;
+        cudaEvent_t done = nullptr;
+        bool used = false;
+    } ws[2];
+    unsigned ws_next = 0;
     // message workspace
     size_t msg_cap = 0, off_cap = 0;
     uint8_t *d_msgs = nullptr;
@@ -94,3 +101,5 @@ int sbv_ensure_workspace(sbv_engine *e, Dev &d, size_t n);
 int sbv_ensure_pinned(sbv_engine *e, Dev &d, size_t bytes);
 int sbv_h2d(sbv_engine *e, Dev &d, void *dst, const void *src, size_t bytes, size_t &stage_off, cudaStream_t st);
 int sbv_ensure_scratch(sbv_engine *e, Dev &d, size_t bytes);
+// takes the next scratch set of device d for a launch on stream st (waits for its previous user)
+int sbv_take_scratch(sbv_engine *e, Dev &d, cudaStream_t st, Dev::Scratch **out);

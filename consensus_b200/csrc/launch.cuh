@@ -14,6 +14,8 @@ int launch_verify_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const u
     const uint32_t nn = (uint32_t)n;
     const uint32_t pthreads = (nn + S - 1) / S;
     const uint32_t pblocks = (pthreads + 127) / 128;
+    Dev::Scratch *w = nullptr;
+    if (int rc = sbv_take_scratch(e, d, st, &w)) return rc;
     cudaEvent_t *ev = nullptr;
     if (e->profiling) {
         if (d.prof_used + 3 > d.prof_events.size()) {
@@ -25,7 +27,7 @@ int launch_verify_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const u
         d.prof_used += 3;
         CU(e, cudaEventRecord(ev[0], st));
     }
-    k_prep<C, W, S><<<pblocks, 128, 0, st>>>(nn, d_r, d_s, d_dig, dlen, d.d_gidx, d.d_digits, d.d_flags);
+    k_prep<C, W, S><<<pblocks, 128, 0, st>>>(nn, d_r, d_s, d_dig, dlen, w->gidx, w->digits, w->flags);
     if (ev) CU(e, cudaEventRecord(ev[1], st));
     const size_t smem = (size_t)TE * 3 * C::N * 4 * BLOCK;
     static bool attr_done = false;
@@ -34,9 +36,10 @@ int launch_verify_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const u
         attr_done = true;
     }
     const uint32_t vblocks = (nn + BLOCK - 1) / BLOCK;
-    k_verify<C, W, BLOCK, MINB><<<vblocks, BLOCK, smem, st>>>(nn, d_qx, d_qy, d_r, d.d_gidx, d.d_digits, d.d_flags,
+    k_verify<C, W, BLOCK, MINB><<<vblocks, BLOCK, smem, st>>>(nn, d_qx, d_qy, d_r, w->gidx, w->digits, w->flags,
                                                         reinterpret_cast<const uint4 *>(d.gtab[curve_idx]), d_ok);
     if (ev) CU(e, cudaEventRecord(ev[2], st));
+    CU(e, cudaEventRecord(w->done, st));
     e->launches += 2;
     CU(e, cudaGetLastError());
     return 0;
