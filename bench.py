@@ -257,21 +257,34 @@ def main():
     value = world * BATCH * args.steps / (dev_ms * 1e-3)
 
     # ---- end-to-end through the C ABI with pinned host buffers ----
+    # Two host threads each keep one synchronous sbv_verify_batch call in flight (the reference calls
+    # its Verifier from concurrent goroutines, view.go:537-541 / consensus.go:302-306); every call does
+    # H2D of its 160 B/item batch, both kernels and the D2H of its verdicts.
     ptr = {k: host[k].data_ptr() for k in fields}
-    def e2e_step():
-        eng.verify_batch_ptr(sbv.P256, BATCH, ptr["r"], ptr["s"], ptr["qx"], ptr["qy"], ptr["digest"], 32, host_ok.data_ptr())
-    for _ in range(args.warmup):
-        e2e_step()
+    host_oks = [torch.zeros(BATCH, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    def e2e_calls(tid, count):
+        for _ in range(count):
+            eng.verify_batch_ptr(sbv.P256, BATCH, ptr["r"], ptr["s"], ptr["qx"], ptr["qy"], ptr["digest"], 32, host_oks[tid].data_ptr())
+    def e2e_run(total):
+        ths = [threading.Thread(target=e2e_calls, args=(t, total // 2 + (t < total % 2))) for t in range(2)]
+        for t in ths: t.start()
+        for t in ths: t.join()
+    e2e_run(2 * args.warmup)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_run(args.steps)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    if not np.array_equal(host_ok.numpy(), want):
-        raise SystemExit("bench: e2e verdicts differ from the oracle")
+    for hk in host_oks:
+        if not np.array_equal(hk.numpy(), want):
+            raise SystemExit("bench: e2e verdicts differ from the oracle")
     e2e_value = world * BATCH * args.steps / e2e_s
+    # one caller, one call at a time: the latency-bound form of the same number
+    host_ok = host_oks[0]
+    t0 = time.perf_counter()
+    e2e_calls(0, 20)
+    e2e_single = world * BATCH * 20 / max_over_ranks(time.perf_counter() - t0)
 
     # ---- registered-key path (extra, NOT the headline): keys registered once with sbv_set_keys, both
     # scalar multiplications fixed-base.  Same signatures; expected verdicts recomputed against the
@@ -344,7 +357,8 @@ def main():
                    "pipelining": "consecutive steps alternate over 2 CUDA streams; unpipelined step latency in step_latency_ms",
                    "exchange": "NCCL all_gather of the packed verdict bitmask per step" if world > 1 else "none (1 GPU)",
                    "sharding": f"batch-parallel x{world}"},
-        "e2e": {"value": e2e_value, "unit": "verifies/s", "h2d_bytes_per_step": 160 * BATCH * world, "d2h_bytes_per_step": BATCH * world},
+        "e2e": {"value": e2e_value, "unit": "verifies/s", "h2d_bytes_per_step": 160 * BATCH * world, "d2h_bytes_per_step": BATCH * world,
+                "callers": 2, "single_caller_value": e2e_single},
         "step_latency_ms": step_latency_ms, "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "registered_keys": reg,
     }
 

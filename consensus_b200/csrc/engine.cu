@@ -152,6 +152,58 @@ __global__ void k_mad_probe(uint32_t *out, uint32_t iters) {
 
 }  // namespace
 int sbv_ensure_workspace(sbv_engine *e, Dev &d, size_t n) { return ensure_workspace(e, d, n); }
+int sbv_lane_acquire(sbv_engine *e) {
+    std::unique_lock<std::mutex> lk(e->mu);
+    e->lane_cv.wait(lk, [&] { return !e->lane_busy[0] || !e->lane_busy[1]; });
+    int lane = e->lane_busy[0] ? 1 : 0;
+    e->lane_busy[lane] = true;
+    return lane;
+}
+void sbv_lane_release(sbv_engine *e, int lane) {
+    { std::lock_guard<std::mutex> lk(e->mu); e->lane_busy[lane] = false; }
+    e->lane_cv.notify_one();
+}
+// caller has set the device.  Only the owner of the lane touches it, so no lock is needed here.
+int sbv_lane_ensure(sbv_engine *e, Dev &d, Dev::Lane &ln, size_t n, size_t pinned_bytes) {
+    if (!ln.stream) CU(e, cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+    if (n > ln.cap) {
+        CU(e, cudaStreamSynchronize(ln.stream));
+        uint8_t **ptrs[] = {&ln.d_r, &ln.d_s, &ln.d_qx, &ln.d_qy, &ln.d_dig, &ln.d_ok};
+        for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+        if (ln.d_slot) cudaFree(ln.d_slot);
+        ln.d_slot = nullptr;
+        const size_t cap = n + n / 8 + 1024;
+        CU(e, cudaMalloc(&ln.d_r, cap * 48));
+        CU(e, cudaMalloc(&ln.d_s, cap * 48));
+        CU(e, cudaMalloc(&ln.d_qx, cap * 48));
+        CU(e, cudaMalloc(&ln.d_qy, cap * 48));
+        CU(e, cudaMalloc(&ln.d_dig, cap * 64));
+        CU(e, cudaMalloc(&ln.d_ok, cap));
+        CU(e, cudaMalloc(&ln.d_slot, cap * 4));
+        ln.cap = cap;
+    }
+    if (pinned_bytes > ln.h_pin_cap) {
+        CU(e, cudaStreamSynchronize(ln.stream));
+        if (ln.h_pin) cudaFreeHost(ln.h_pin);
+        ln.h_pin = nullptr;
+        const size_t cap = pinned_bytes + pinned_bytes / 4 + 4096;
+        CU(e, cudaHostAlloc(&ln.h_pin, cap, cudaHostAllocPortable));
+        ln.h_pin_cap = cap;
+    }
+    (void)d;
+    return 0;
+}
+int sbv_lane_h2d(sbv_engine *e, Dev::Lane &ln, void *dst, const void *src, size_t bytes, size_t &stage_off) {
+    if (bytes == 0) return 0;
+    if (is_pinned(src)) {
+        CU(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ln.stream));
+    } else {
+        memcpy(ln.h_pin + stage_off, src, bytes);
+        CU(e, cudaMemcpyAsync(dst, ln.h_pin + stage_off, bytes, cudaMemcpyHostToDevice, ln.stream));
+        stage_off += (bytes + 255) & ~(size_t)255;
+    }
+    return 0;
+}
 int sbv_take_scratch(sbv_engine *e, Dev &d, cudaStream_t st, Dev::Scratch **out) {
     Dev::Scratch &w = d.ws[d.ws_next++ & 1];
     if (w.used) CU(e, cudaStreamWaitEvent(st, w.done, 0));
@@ -215,7 +267,7 @@ Shard shard_of(size_t n, int g, int G) {
 // g * words_per.
 size_t words_per_shard(size_t n, int G) { return (((n + G - 1) / G) + 31) / 32; }
 
-int gather_verdicts(sbv_engine *e, size_t n, uint8_t *ok_host) {
+int gather_verdicts(sbv_engine *e, size_t n, int lane) {
     const int G = (int)e->devs.size();
     const size_t wp = words_per_shard(n, G);
     for (int g = 0; g < G; g++) {
@@ -224,10 +276,12 @@ int gather_verdicts(sbv_engine *e, size_t n, uint8_t *ok_host) {
         int rc = sbv_ensure_scratch(e, d, wp * G * 4);
         if (rc) return rc;
         Shard sh = shard_of(n, g, G);
+        Dev::Lane &ln = d.lanes[lane];
+        if (!ln.stream) CU(e, cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
         uint32_t *mine = (uint32_t *)d.d_scratch + wp * g;
-        CU(e, cudaMemsetAsync(mine, 0, wp * 4, d.stream));
+        CU(e, cudaMemsetAsync(mine, 0, wp * 4, ln.stream));
         if (sh.n) {
-            k_pack_bits<<<(uint32_t)((sh.n + 255) / 256), 256, 0, d.stream>>>((uint32_t)sh.n, d.d_ok, mine);
+            k_pack_bits<<<(uint32_t)((sh.n + 255) / 256), 256, 0, ln.stream>>>((uint32_t)sh.n, ln.d_ok, mine);
             e->launches += 1;
             CU(e, cudaGetLastError());
         }
@@ -236,14 +290,13 @@ int gather_verdicts(sbv_engine *e, size_t n, uint8_t *ok_host) {
     for (int g = 0; g < G; g++) {
         Dev &d = e->devs[g];
         uint32_t *buf = (uint32_t *)d.d_scratch;
-        NC(e, g_nccl.all_gather(buf + wp * g, buf, wp, NCCL_UINT32, e->nccl_comms[g], d.stream));
+        NC(e, g_nccl.all_gather(buf + wp * g, buf, wp, NCCL_UINT32, e->nccl_comms[g], d.lanes[lane].stream));
     }
     NC(e, g_nccl.group_end());
     Dev &d0 = e->devs[0];
     CU(e, cudaSetDevice(d0.ordinal));
-    (void)ok_host;
     e->gather_words.resize(wp * G);
-    CU(e, cudaMemcpyAsync(e->gather_words.data(), d0.d_scratch, wp * G * 4, cudaMemcpyDeviceToHost, d0.stream));
+    CU(e, cudaMemcpyAsync(e->gather_words.data(), d0.d_scratch, wp * G * 4, cudaMemcpyDeviceToHost, d0.lanes[lane].stream));
     return 0;
 }
 
@@ -307,6 +360,13 @@ void sbv_destroy(sbv_engine *e) {
         for (auto &w : d.ws) if (w.done) cudaEventDestroy(w.done);
         for (void *p : ptrs) if (p) cudaFree(p);
         sbv_keys_free(d);
+        for (auto &ln : d.lanes) {
+            if (ln.stream) cudaStreamSynchronize(ln.stream);
+            void *lp[] = {ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, ln.d_ok, ln.d_slot};
+            for (void *p : lp) if (p) cudaFree(p);
+            if (ln.h_pin) cudaFreeHost(ln.h_pin);
+            if (ln.stream) cudaStreamDestroy(ln.stream);
+        }
         if (d.h_pin) cudaFreeHost(d.h_pin);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
@@ -346,37 +406,48 @@ int sbv_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *r, c
         return fail(e, SBV_ERR_ARG, "sbv_verify_batch: bad argument");
     if (n == 0) return SBV_OK;
     if (!r || !s || !qx || !qy || !digest || !ok) return fail(e, SBV_ERR_ARG, "null buffer");
-    std::lock_guard<std::mutex> lk(e->mu);
+    if (n > 0x7fffffffu) return fail(e, SBV_ERR_ARG, "n too large");
     const size_t L = fbytes(curve);
     const int G = (int)e->devs.size();
+    // A call owns one lane (stream + buffers) on every device; the engine lock is held only while
+    // kernels are enqueued, so a second host thread overlaps its copies and kernels with ours.
+    const int lane = sbv_lane_acquire(e);
+    struct Release { sbv_engine *e; int lane; ~Release() { sbv_lane_release(e, lane); } } release{e, lane};
     for (int g = 0; g < G; g++) {
         Dev &d = e->devs[g];
+        Dev::Lane &ln = d.lanes[lane];
         Shard sh = shard_of(n, g, G);
         if (sh.n == 0) continue;
         CU(e, cudaSetDevice(d.ordinal));
-        int rc = ensure_workspace(e, d, sh.n);
-        if (rc) return rc;
-        rc = ensure_pinned(e, d, sh.n * (4 * L + digest_len + 1) + 8 * 256);
+        int rc = sbv_lane_ensure(e, d, ln, sh.n, sh.n * (4 * L + digest_len + 1) + 8 * 256);
         if (rc) return rc;
         size_t so = 0;
-        if ((rc = h2d(e, d, d.d_r, r + sh.lo * L, sh.n * L, so, d.stream))) return rc;
-        if ((rc = h2d(e, d, d.d_s, s + sh.lo * L, sh.n * L, so, d.stream))) return rc;
-        if ((rc = h2d(e, d, d.d_qx, qx + sh.lo * L, sh.n * L, so, d.stream))) return rc;
-        if ((rc = h2d(e, d, d.d_qy, qy + sh.lo * L, sh.n * L, so, d.stream))) return rc;
-        if ((rc = h2d(e, d, d.d_dig, digest + sh.lo * digest_len, sh.n * digest_len, so, d.stream))) return rc;
-        rc = launch_verify(e, d, curve, sh.n, d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, digest_len, d.d_ok, d.stream);
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_r, r + sh.lo * L, sh.n * L, so))) return rc;
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_s, s + sh.lo * L, sh.n * L, so))) return rc;
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_dig, digest + sh.lo * digest_len, sh.n * digest_len, so))) return rc;
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_qx, qx + sh.lo * L, sh.n * L, so))) return rc;
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_qy, qy + sh.lo * L, sh.n * L, so))) return rc;
+        {
+            std::lock_guard<std::mutex> lk(e->mu);
+            rc = ensure_workspace(e, d, sh.n);
+            if (!rc) rc = launch_verify(e, d, curve, sh.n, ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, digest_len, ln.d_ok, ln.stream);
+        }
         if (rc) return rc;
-        if (G == 1) CU(e, cudaMemcpyAsync(ok + sh.lo, d.d_ok, sh.n, cudaMemcpyDeviceToHost, d.stream));
+        if (G == 1) CU(e, cudaMemcpyAsync(ok + sh.lo, ln.d_ok, sh.n, cudaMemcpyDeviceToHost, ln.stream));
     }
     if (G > 1) {
-        int rc = gather_verdicts(e, n, ok);
+        std::lock_guard<std::mutex> lk(e->mu);  // the gather buffers are per device, not per lane
+        int rc = gather_verdicts(e, n, lane);
         if (rc) return rc;
+        for (int g = 0; g < G; g++) {
+            CU(e, cudaSetDevice(e->devs[g].ordinal));
+            CU(e, cudaStreamSynchronize(e->devs[g].lanes[lane].stream));
+        }
+        unpack_verdicts(e, n, ok);
+        return SBV_OK;
     }
-    for (int g = 0; g < G; g++) {
-        CU(e, cudaSetDevice(e->devs[g].ordinal));
-        CU(e, cudaStreamSynchronize(e->devs[g].stream));
-    }
-    if (G > 1) unpack_verdicts(e, n, ok);
+    CU(e, cudaSetDevice(e->devs[0].ordinal));
+    CU(e, cudaStreamSynchronize(e->devs[0].lanes[lane].stream));
     return SBV_OK;
 }
 

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdint>
+#include <condition_variable>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -28,6 +29,16 @@ struct Dev {
         bool used = false;
     } ws[2];
     unsigned ws_next = 0;
+    // per-call lanes of the host-buffer entry points: own stream, input/verdict buffers and pinned staging, so
+    // two host threads can have a call in flight each (H2D / kernels / D2H of one overlap the other's)
+    struct Lane {
+        cudaStream_t stream = nullptr;
+        size_t cap = 0;
+        uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr, *d_qy = nullptr, *d_dig = nullptr, *d_ok = nullptr;
+        uint32_t *d_slot = nullptr;
+        uint8_t *h_pin = nullptr;
+        size_t h_pin_cap = 0;
+    } lanes[2];
     // message workspace
     size_t msg_cap = 0, off_cap = 0;
     uint8_t *d_msgs = nullptr;
@@ -53,6 +64,8 @@ struct Dev {
 struct sbv_engine {
     std::vector<Dev> devs;
     std::mutex mu;
+    std::condition_variable lane_cv;
+    bool lane_busy[2] = {false, false};
     std::string err;
     uint64_t launches = 0;
     int p256_w = 4, p256_block = 128, p384_w = 3, p384_block = 128;
@@ -100,6 +113,10 @@ int sbv_launch_keyed(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint3
 int sbv_ensure_workspace(sbv_engine *e, Dev &d, size_t n);
 int sbv_ensure_pinned(sbv_engine *e, Dev &d, size_t bytes);
 int sbv_h2d(sbv_engine *e, Dev &d, void *dst, const void *src, size_t bytes, size_t &stage_off, cudaStream_t st);
+int sbv_lane_acquire(sbv_engine *e);            // blocks until a lane index is free; returns it
+void sbv_lane_release(sbv_engine *e, int lane);
+int sbv_lane_ensure(sbv_engine *e, Dev &d, Dev::Lane &ln, size_t n, size_t pinned_bytes);
+int sbv_lane_h2d(sbv_engine *e, Dev::Lane &ln, void *dst, const void *src, size_t bytes, size_t &stage_off);
 int sbv_ensure_scratch(sbv_engine *e, Dev &d, size_t bytes);
 // takes the next scratch set of device d for a launch on stream st (waits for its previous user)
 int sbv_take_scratch(sbv_engine *e, Dev &d, cudaStream_t st, Dev::Scratch **out);

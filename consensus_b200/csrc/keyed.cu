@@ -21,7 +21,7 @@ void sbv_keys_free(Dev &d) {
 
 int sbv_keys_build(sbv_engine *e, Dev &d) {
     CU(e, cudaSetDevice(d.ordinal));
-    CU(e, cudaStreamSynchronize(d.stream));
+    CU(e, cudaDeviceSynchronize());  // no launch on any lane may still read the old tables
     sbv_keys_free(d);
     const size_t n = e->key_ids.size();
     d.n_slots = (uint32_t)n;
@@ -128,36 +128,34 @@ int sbv_verify_registered(sbv_engine *e, uint8_t curve, size_t n, const uint32_t
     if (n == 0) return SBV_OK;
     if (!key_slot || !r || !s || !digest || !ok) return sbv_fail(e, SBV_ERR_ARG, "null buffer");
     if (n > 0x7fffffffu) return sbv_fail(e, SBV_ERR_ARG, "n too large");
-    std::lock_guard<std::mutex> lk(e->mu);
     const size_t L = curve == SBV_P256 ? 32 : 48;
     const int G = (int)e->devs.size();
+    const int lane = sbv_lane_acquire(e);
+    struct Release { sbv_engine *e; int lane; ~Release() { sbv_lane_release(e, lane); } } release{e, lane};
     for (int g = 0; g < G; g++) {
         Dev &d = e->devs[g];
+        Dev::Lane &ln = d.lanes[lane];
         const size_t lo = n * g / G, cnt = n * (g + 1) / G - lo;
         if (cnt == 0) continue;
         CU(e, cudaSetDevice(d.ordinal));
-        int rc = sbv_ensure_workspace(e, d, cnt);
-        if (rc) return rc;
-        if (cnt > d.slot_cap) {
-            if (d.d_slot) cudaFree(d.d_slot);
-            d.d_slot = nullptr;
-            d.slot_cap = cnt + cnt / 8 + 1024;
-            CU(e, cudaMalloc(&d.d_slot, d.slot_cap * 4));
-        }
-        rc = sbv_ensure_pinned(e, d, cnt * (2 * L + digest_len + 5) + 8 * 256);
+        int rc = sbv_lane_ensure(e, d, ln, cnt, cnt * (2 * L + digest_len + 5) + 8 * 256);
         if (rc) return rc;
         size_t so = 0;
-        if ((rc = sbv_h2d(e, d, d.d_slot, key_slot + lo, cnt * 4, so, d.stream))) return rc;
-        if ((rc = sbv_h2d(e, d, d.d_r, r + lo * L, cnt * L, so, d.stream))) return rc;
-        if ((rc = sbv_h2d(e, d, d.d_s, s + lo * L, cnt * L, so, d.stream))) return rc;
-        if ((rc = sbv_h2d(e, d, d.d_dig, digest + lo * digest_len, cnt * digest_len, so, d.stream))) return rc;
-        rc = sbv_launch_keyed(e, d, curve, cnt, d.d_slot, d.d_r, d.d_s, d.d_dig, digest_len, d.d_ok, d.stream);
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_slot, key_slot + lo, cnt * 4, so))) return rc;
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_r, r + lo * L, cnt * L, so))) return rc;
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_s, s + lo * L, cnt * L, so))) return rc;
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_dig, digest + lo * digest_len, cnt * digest_len, so))) return rc;
+        {
+            std::lock_guard<std::mutex> lk(e->mu);
+            rc = sbv_ensure_workspace(e, d, cnt);
+            if (!rc) rc = sbv_launch_keyed(e, d, curve, cnt, ln.d_slot, ln.d_r, ln.d_s, ln.d_dig, digest_len, ln.d_ok, ln.stream);
+        }
         if (rc) return rc;
-        CU(e, cudaMemcpyAsync(ok + lo, d.d_ok, cnt, cudaMemcpyDeviceToHost, d.stream));
+        CU(e, cudaMemcpyAsync(ok + lo, ln.d_ok, cnt, cudaMemcpyDeviceToHost, ln.stream));
     }
     for (int g = 0; g < G; g++) {
         CU(e, cudaSetDevice(e->devs[g].ordinal));
-        CU(e, cudaStreamSynchronize(e->devs[g].stream));
+        if (e->devs[g].lanes[lane].stream) CU(e, cudaStreamSynchronize(e->devs[g].lanes[lane].stream));
     }
     return SBV_OK;
 }

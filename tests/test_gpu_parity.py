@@ -269,3 +269,23 @@ def test_registered_key_path_bit_exact(eng, curve):
     assert (generic == got[sel]).all()
     eng.set_keys(np.zeros(0, np.uint8), np.zeros((0, 96), np.uint8))      # empty registry: everything rejects
     assert eng.verify_registered(curve, slot[:50], r[:50], s[:50], dig[:50]).sum() == 0
+
+
+def test_concurrent_callers_share_the_engine(eng):
+    """Two host threads each keep a synchronous call in flight (per-call lanes); verdicts stay exact."""
+    import threading
+    bs = [corpus.make_batch(P256, n=6000 + 37 * k, K=8, seed=101 + k, corrupt_rate=3) for k in range(4)]
+    wants = [oracle.verify_batch(P256, b["r"], b["s"], b["qx"], b["qy"], b["digest"]) for b in bs]
+    errs = []
+    def worker(k):
+        try:
+            for _ in range(6):
+                got = eng.verify_batch(P256, bs[k]["r"], bs[k]["s"], bs[k]["qx"], bs[k]["qy"], bs[k]["digest"])
+                if not (got == wants[k]).all():
+                    errs.append(k)
+        except Exception as ex:  # noqa: BLE001
+            errs.append(repr(ex))
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in ths: t.start()
+    for t in ths: t.join()
+    assert not errs, errs
