@@ -134,6 +134,10 @@ static __device__ __noinline__ Fe8 p256_fsqr_call(Fe8 a) {
 // -------------------------------------------------------------------------------------------------
 // P-384: generic word-serial Montgomery for both fields (12 limbs).
 // -------------------------------------------------------------------------------------------------
+struct Fe12 { uint32_t v[12]; };
+static __device__ __noinline__ Fe12 p384_fmul_call(Fe12 a, Fe12 b);
+static __device__ __noinline__ Fe12 p384_fsqr_call(Fe12 a);
+
 struct P384 {
     static constexpr int N = 12;
     static constexpr int BYTES = 48;
@@ -153,11 +157,27 @@ struct P384 {
     SBV_DEV static uint32_t p_minus_2_limb(int i) { const uint32_t c[12] = SBV_P384_P_MINUS_2; return c[i]; }
     SBV_DEV static uint32_t n_minus_2_limb(int i) { const uint32_t c[12] = SBV_P384_N_MINUS_2; return c[i]; }
 
-    SBV_DEV static void fmul(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
+    SBV_DEV static void fmul_inline(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
         const uint32_t p[12] = SBV_P384_P;
         mont_mul_generic<12>(r, a, b, p, SBV_P384_PINV);
     }
-    SBV_DEV static void fsqr(uint32_t (&r)[12], const uint32_t (&a)[12]) { fmul(r, a, a); }
+    SBV_DEV static void fsqr_inline(uint32_t (&r)[12], const uint32_t (&a)[12]) {
+        const uint32_t p[12] = SBV_P384_P;
+        mont_sqr_generic<12>(r, a, p, SBV_P384_PINV);
+    }
+    // out of line, operands in registers — same reason as P256::fmul
+    SBV_DEV static void fmul(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
+        Fe12 x, y;
+        mp_copy<12>(x.v, a); mp_copy<12>(y.v, b);
+        Fe12 z = p384_fmul_call(x, y);
+        mp_copy<12>(r, z.v);
+    }
+    SBV_DEV static void fsqr(uint32_t (&r)[12], const uint32_t (&a)[12]) {
+        Fe12 x;
+        mp_copy<12>(x.v, a);
+        Fe12 z = p384_fsqr_call(x);
+        mp_copy<12>(r, z.v);
+    }
     SBV_DEV static void fhalf(uint32_t (&r)[12], const uint32_t (&a)[12]) {
         const uint32_t p[12] = SBV_P384_P;
         const uint32_t mask = 0u - (a[0] & 1u);
@@ -183,6 +203,17 @@ struct P384 {
         mont_mul_generic<12>(r, a, b, n, SBV_P384_NINV);
     }
 };
+
+static __device__ __noinline__ Fe12 p384_fmul_call(Fe12 a, Fe12 b) {
+    Fe12 r;
+    P384::fmul_inline(r.v, a.v, b.v);
+    return r;
+}
+static __device__ __noinline__ Fe12 p384_fsqr_call(Fe12 a) {
+    Fe12 r;
+    P384::fsqr_inline(r.v, a.v);
+    return r;
+}
 
 // -------------------------------------------------------------------------------------------------
 // Jacobian points (X, Y, Z) ~ (X/Z^2, Y/Z^3); Z == 0 is the point at infinity.

@@ -130,7 +130,7 @@ int launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t 
     if (curve == SBV_P256) {
         return sbv_launch_p256_w3_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
     }
-    return sbv_launch_p384_w3_b128(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
+    return sbv_launch_p384_w3_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
 }
 
 __global__ void k_mad_probe(uint32_t *out, uint32_t iters) {

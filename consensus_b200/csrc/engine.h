@@ -103,7 +103,7 @@ inline int sbv_fail(sbv_engine *e, int code, const char *fmt, ...) {
 // per-(curve, window, block) kernel launchers — one translation unit each (inst_*.cu)
 int sbv_launch_p256_w3_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                            const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
-int sbv_launch_p384_w3_b128(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
+int sbv_launch_p384_w3_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                             const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
 int sbv_init_gtables(sbv_engine *e, Dev &d);  // gtable.cu
 int sbv_keys_build(sbv_engine *e, Dev &d);    // keyed.cu: (re)builds the per-key comb tables from the registry

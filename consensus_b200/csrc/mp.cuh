@@ -183,18 +183,14 @@ SBV_DEV void mod_sub(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&
     r[N - 1] = addc(d[N - 1], m[N - 1] & mask);
 }
 
-// Generic word-serial Montgomery product r = a*b*2^(-32N) mod m, minv = -m^-1 mod 2^32.
-// a, b < m.  Used for arithmetic mod the group order n and for the P-384 field.
+// Generic word-serial Montgomery reduction: r = T * 2^(-32N) mod m for T < m * 2^(32N),
+// minv = -m^-1 mod 2^32.  Used for arithmetic mod the group order n and for the P-384 field.
 template <int N>
-SBV_DEV void mont_mul_generic(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&b)[N],
-                              const uint32_t (&m)[N], uint32_t minv) {
-    uint32_t T[2 * N];
-    mp_mul<N>(T, a, b);
+SBV_DEV void mont_reduce_generic(uint32_t (&r)[N], uint32_t (&T)[2 * N], const uint32_t (&m)[N], uint32_t minv) {
     uint32_t top = 0;  // carry limb above T[2N-1]
 #pragma unroll
     for (int i = 0; i < N; i++) {
         uint32_t q = T[i] * minv;
-        // T[i..i+N] += q*m  (even/odd would need two accumulators; a 64-bit carry walk is fine here)
         uint64_t c = 0;
 #pragma unroll
         for (int j = 0; j < N; j++) {
@@ -202,7 +198,6 @@ SBV_DEV void mont_mul_generic(uint32_t (&r)[N], const uint32_t (&a)[N], const ui
             T[i + j] = (uint32_t)v;
             c = v >> 32;
         }
-        // propagate c upward
 #pragma unroll
         for (int j = i + N; j < 2 * N; j++) {
             uint64_t v = (uint64_t)T[j] + c;
@@ -217,6 +212,18 @@ SBV_DEV void mont_mul_generic(uint32_t (&r)[N], const uint32_t (&a)[N], const ui
     uint32_t bw = mp_sub<N>(t, hi, m);
     bool use_t = (top != 0) || (bw == 0);
     mp_select<N>(r, use_t, t, hi);
+}
+template <int N>
+SBV_DEV void mont_mul_generic(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&b)[N], const uint32_t (&m)[N], uint32_t minv) {
+    uint32_t T[2 * N];
+    mp_mul<N>(T, a, b);
+    mont_reduce_generic<N>(r, T, m, minv);
+}
+template <int N>
+SBV_DEV void mont_sqr_generic(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&m)[N], uint32_t minv) {
+    uint32_t T[2 * N];
+    mp_sqr<N>(T, a);
+    mont_reduce_generic<N>(r, T, m, minv);
 }
 
 }  // namespace sbv
