@@ -251,12 +251,13 @@ SBV_DEV void pt_double(Jac<C> &P) {
     C::fsub(P.Y, t2, bb);       // Y3
 }
 
-// P += (x2, y2[, z2]).  AFFINE: z2 == 1 (mixed add, 8M+3S) else general (12M+4S).
+// P += (x2, y2[, z2]).  MODE 1: z2 == 1 (mixed add, 8M+3S).  MODE 0: general (12M+4S).
+// MODE 2: z2 with its square and cube supplied (table points sharing one Z: 11M+3S).
 // `skip` leaves P unchanged (digit 0).  `neg` adds the negated point.  Handles every exceptional
 // case: P = inf -> result is the addend; P == addend -> doubling; P == -addend -> infinity (Z3 = 0).
-template <class C, bool AFFINE>
-SBV_DEV void pt_add(Jac<C> &P, const uint32_t (&x2)[C::N], const uint32_t (&y2_in)[C::N],
-                    const uint32_t (&z2)[C::N], bool neg, bool skip) {
+template <class C, int MODE>
+SBV_DEV void pt_add_m(Jac<C> &P, const uint32_t (&x2)[C::N], const uint32_t (&y2_in)[C::N], const uint32_t (&z2)[C::N],
+                      const uint32_t (&z2sq)[C::N], const uint32_t (&z2cu)[C::N], bool neg, bool skip) {
     constexpr int N = C::N;
     uint32_t y2[N], zero[N];
 #pragma unroll
@@ -272,9 +273,12 @@ SBV_DEV void pt_add(Jac<C> &P, const uint32_t (&x2)[C::N], const uint32_t (&y2_i
     C::fmul(u2, x2, z1z1);
     C::fmul(t, P.Z, z1z1);
     C::fmul(s2, y2, t);
-    if (AFFINE) {
+    if (MODE == 1) {
         mp_copy<N>(u1, P.X);
         mp_copy<N>(s1, P.Y);
+    } else if (MODE == 2) {
+        C::fmul(u1, P.X, z2sq);
+        C::fmul(s1, P.Y, z2cu);
     } else {
         uint32_t z2z2[N];
         C::fsqr(z2z2, z2);
@@ -302,18 +306,50 @@ SBV_DEV void pt_add(Jac<C> &P, const uint32_t (&x2)[C::N], const uint32_t (&y2_i
     C::fmul(t, s1, hhh);
     C::fsub(y3, y3, t);
     C::fmul(z3, P.Z, h);
-    if (!AFFINE) C::fmul(z3, z3, z2);
+    if (MODE != 1) C::fmul(z3, z3, z2);
     // select: skip -> P ; P inf -> addend ; else sum
     uint32_t one[N];
     C::get_one(one);
 #pragma unroll
     for (int i = 0; i < N; i++) {
-        uint32_t ax = x2[i], ay = y2[i], az = AFFINE ? one[i] : z2[i];
+        uint32_t ax = x2[i], ay = y2[i], az = MODE == 1 ? one[i] : z2[i];
         uint32_t nx = p_inf ? ax : x3[i], ny = p_inf ? ay : y3[i], nz = p_inf ? az : z3[i];
         P.X[i] = skip ? P.X[i] : nx;
         P.Y[i] = skip ? P.Y[i] : ny;
         P.Z[i] = skip ? P.Z[i] : nz;
     }
+}
+template <class C, bool AFFINE>
+SBV_DEV void pt_add(Jac<C> &P, const uint32_t (&x2)[C::N], const uint32_t (&y2)[C::N], const uint32_t (&z2)[C::N], bool neg, bool skip) {
+    if (AFFINE) pt_add_m<C, 1>(P, x2, y2, z2, z2, z2, neg, skip);
+    else pt_add_m<C, 0>(P, x2, y2, z2, z2, z2, neg, skip);
+}
+
+// Table construction step: P += (qx, qy) affine, with P = k*(qx, qy), k >= 2 (no exceptional case can
+// occur: the group order is prime and huge).  Also returns H = Z3 / Z1, the factor the co-Z
+// normalisation needs.
+template <class C>
+SBV_DEV void pt_madd_table(Jac<C> &P, const uint32_t (&qx)[C::N], const uint32_t (&qy)[C::N], uint32_t (&h)[C::N]) {
+    constexpr int N = C::N;
+    uint32_t z1z1[N], u2[N], s2[N], r[N], t[N], hh[N], hhh[N], v[N];
+    C::fsqr(z1z1, P.Z);
+    C::fmul(u2, qx, z1z1);
+    C::fmul(t, P.Z, z1z1);
+    C::fmul(s2, qy, t);
+    C::fsub(h, u2, P.X);
+    C::fsub(r, s2, P.Y);
+    C::fsqr(hh, h);
+    C::fmul(hhh, h, hh);
+    C::fmul(v, P.X, hh);
+    C::fmul(t, P.Y, hhh);   // Y1 * H^3
+    C::fsqr(P.X, r);
+    C::fsub(P.X, P.X, hhh);
+    C::fsub(P.X, P.X, v);
+    C::fsub(P.X, P.X, v);
+    C::fsub(v, v, P.X);
+    C::fmul(P.Y, r, v);
+    C::fsub(P.Y, P.Y, t);
+    C::fmul(P.Z, P.Z, h);
 }
 
 // r = a^(p-2) (field inverse, Montgomery in/out); a != 0.  Setup paths only.

@@ -39,6 +39,8 @@ int ensure_workspace(sbv_engine *e, Dev &d, size_t n) {
         if (w.gidx) cudaFree(w.gidx);
         if (w.digits) cudaFree(w.digits);
         if (w.flags) cudaFree(w.flags);
+        if (w.tscr) cudaFree(w.tscr);
+        w.tscr = nullptr;
         w.gidx = nullptr; w.digits = nullptr; w.flags = nullptr; w.used = false;
         if (!w.done) CU(e, cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
     }
@@ -52,6 +54,7 @@ int ensure_workspace(sbv_engine *e, Dev &d, size_t n) {
         CU(e, cudaMalloc(&w.gidx, cap * 48 * sizeof(uint16_t)));
         CU(e, cudaMalloc(&w.flags, cap));
         CU(e, cudaMalloc(&w.digits, cap * 132));
+        CU(e, cudaMalloc(&w.tscr, cap * 12 * 8 * sizeof(uint32_t)));
     }
     d.cap = cap;
     return 0;
@@ -128,6 +131,7 @@ int launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t 
                   cudaStream_t st) {
     if (n == 0) return 0;
     if (curve == SBV_P256) {
+        if (e->p256_variant == 1) return sbv_launch_p256_coz_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
         return sbv_launch_p256_w3_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
     }
     return sbv_launch_p384_w3_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
@@ -321,6 +325,7 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count < n_devices) return SBV_ERR_CUDA;
     sbv_engine *e = new sbv_engine();
+    e->p256_variant = env_int("SBV_P256_VARIANT", 1);
     e->devs.resize(n_devices);
     for (int g = 0; g < n_devices; g++) {
         Dev &d = e->devs[g];
@@ -355,7 +360,7 @@ void sbv_destroy(sbv_engine *e) {
     for (Dev &d : e->devs) {
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        void *ptrs[] = {d.gtab[0], d.gtab[1], d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, d.d_ok, d.ws[0].gidx, d.ws[0].flags, d.ws[0].digits,
+        void *ptrs[] = {d.gtab[0], d.gtab[1], d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, d.d_ok, d.ws[0].gidx, d.ws[0].flags, d.ws[0].digits, d.ws[0].tscr, d.ws[1].tscr,
                         d.ws[1].gidx, d.ws[1].flags, d.ws[1].digits, d.d_msgs, d.d_off, d.d_scratch};
         for (auto &w : d.ws) if (w.done) cudaEventDestroy(w.done);
         for (void *p : ptrs) if (p) cudaFree(p);

@@ -25,6 +25,7 @@ struct Dev {
         uint16_t *gidx = nullptr;
         int8_t *digits = nullptr;
         uint8_t *flags = nullptr;
+        uint32_t *tscr = nullptr;  // k_verify_coz per-signature scratch: 12N words, word-major
         cudaEvent_t done = nullptr;
         bool used = false;
     } ws[2];
@@ -68,7 +69,7 @@ struct sbv_engine {
     bool lane_busy[2] = {false, false};
     std::string err;
     uint64_t launches = 0;
-    int p256_w = 4, p256_block = 128, p384_w = 3, p384_block = 128;
+    int p256_variant = 1;  // 1 = co-Z 4-bit window (default), 0 = 3-bit Jacobian window (SBV_P256_VARIANT=0)
     bool profiling = false;
     // NCCL (multi-device only; loaded lazily with dlopen so single-device users never touch it)
     void *nccl_lib = nullptr;
@@ -103,6 +104,8 @@ inline int sbv_fail(sbv_engine *e, int code, const char *fmt, ...) {
 // per-(curve, window, block) kernel launchers — one translation unit each (inst_*.cu)
 int sbv_launch_p256_w3_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                            const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
+int sbv_launch_p256_coz_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
+                            const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
 int sbv_launch_p384_w3_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                             const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
 int sbv_init_gtables(sbv_engine *e, Dev &d);  // gtable.cu

@@ -434,4 +434,165 @@ __global__ void __launch_bounds__(BLOCK) k_verify_keyed(uint32_t n, const uint32
     ok_out[idx] = (good && match) ? 1 : 0;
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_verify_coz — generic path with a 4-bit signed window over a COMMON-Z table of Q.
+// The eight multiples k*Q are brought to one shared Z (Zc), so a table entry is 64 bytes: 2Q..8Q
+// live in shared memory (448 B per thread, bank = lane), 1Q and Zc, Zc^2, Zc^3 in a coalesced global
+// scratch (tscr[40][n]).  65 additions of 11M+3S instead of the 86 of 12M+4S a 3-bit Jacobian table
+// needs at the same single-wave occupancy (7 blocks of 64 threads per SM).
+template <class C, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_verify_coz(uint32_t n, const uint8_t *__restrict__ qx_be, const uint8_t *__restrict__ qy_be,
+                                                             const uint8_t *__restrict__ r_be, const uint16_t *__restrict__ gidx,
+                                                             const int8_t *__restrict__ digits, const uint8_t *__restrict__ flags,
+                                                             const uint4 *__restrict__ gtab, uint32_t *__restrict__ tscr,
+                                                             uint8_t *__restrict__ ok_out) {
+    constexpr int N = C::N;
+    constexpr int W = 4;
+    constexpr int NWIN = Windows<32 * N, W>::COUNT;
+    extern __shared__ uint32_t tab[];  // entries 2..8: [((k-2)*2 + coord)*N + limb][BLOCK]
+    const uint32_t tid = threadIdx.x;
+    const uint32_t idx = blockIdx.x * BLOCK + tid;
+    if (idx >= n) return;
+#define TAB(k, c, w) tab[((((k) - 2) * 2 + (c)) * N + (w)) * BLOCK + tid]
+#define SCR(w) tscr[(size_t)(w) * n + idx]
+    // scratch words: [0,2N) entry 1 (x, y) ; [2N,3N) Zc ; [3N,4N) Zc^2 ; [4N,5N) Zc^3 ; [5N, 12N) H_2..H_8
+    uint32_t pmod[N], one[N];
+    C::get_p(pmod);
+    C::get_one(one);
+    bool good = flags[idx] != 0;
+    {
+        uint32_t x[N], y[N], rr[N], qxm[N], qym[N];
+        load_be<N>(x, qx_be + (size_t)idx * C::BYTES);
+        load_be<N>(y, qy_be + (size_t)idx * C::BYTES);
+        good = good && mp_lt<N>(x, pmod) && mp_lt<N>(y, pmod);
+        C::get_rr_p(rr);
+        C::fmul(qxm, x, rr);
+        C::fmul(qym, y, rr);
+        {
+            uint32_t lhs[N], rhs[N], t[N], b[N];
+            C::fsqr(lhs, qym);
+            C::fsqr(t, qxm);
+            C::fmul(rhs, t, qxm);
+            C::fsub(rhs, rhs, qxm); C::fsub(rhs, rhs, qxm); C::fsub(rhs, rhs, qxm);
+            C::get_b(b);
+            C::fadd(rhs, rhs, b);
+            good = good && mp_eq<N>(lhs, rhs);
+        }
+        // forward: T_k = k*Q in Jacobian; keep (X_k, Y_k) and the ratio H_k = Z_k / Z_{k-1}
+        Jac<C> P;
+        mp_copy<N>(P.X, qxm); mp_copy<N>(P.Y, qym); mp_copy<N>(P.Z, one);
+        pt_double<C>(P);  // T_2, Z_2 = 2*y  (ratio to Z_1 = 1)
+#pragma unroll
+        for (int i = 0; i < N; i++) { TAB(2, 0, i) = P.X[i]; TAB(2, 1, i) = P.Y[i]; SCR(5 * N + i) = P.Z[i]; }
+#pragma unroll 1
+        for (int k = 3; k <= 8; k++) {
+            uint32_t h[N];
+            pt_madd_table<C>(P, qxm, qym, h);
+#pragma unroll
+            for (int i = 0; i < N; i++) { TAB(k, 0, i) = P.X[i]; TAB(k, 1, i) = P.Y[i]; SCR((5 + k - 2) * N + i) = h[i]; }
+        }
+        // common Z = Z_8
+        {
+            uint32_t z2[N], z3[N];
+            C::fsqr(z2, P.Z);
+            C::fmul(z3, z2, P.Z);
+#pragma unroll
+            for (int i = 0; i < N; i++) { SCR(2 * N + i) = P.Z[i]; SCR(3 * N + i) = z2[i]; SCR(4 * N + i) = z3[i]; }
+        }
+        // backward: c_j = Z_8 / Z_j = H_{j+1} * ... * H_8 ; (X_j, Y_j) *= (c_j^2, c_j^3)
+        uint32_t cacc[N];
+        mp_copy<N>(cacc, one);
+#pragma unroll 1
+        for (int j = 7; j >= 1; j--) {
+            uint32_t h[N], c2[N], c3[N], xx[N], yy[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) h[i] = SCR((5 + j + 1 - 2) * N + i);
+            C::fmul(cacc, cacc, h);
+            C::fsqr(c2, cacc);
+            C::fmul(c3, c2, cacc);
+            if (j >= 2) {
+#pragma unroll
+                for (int i = 0; i < N; i++) { xx[i] = TAB(j, 0, i); yy[i] = TAB(j, 1, i); }
+            } else {
+                mp_copy<N>(xx, qxm); mp_copy<N>(yy, qym);
+            }
+            C::fmul(xx, xx, c2);
+            C::fmul(yy, yy, c3);
+            if (j >= 2) {
+#pragma unroll
+                for (int i = 0; i < N; i++) { TAB(j, 0, i) = xx[i]; TAB(j, 1, i) = yy[i]; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; i++) { SCR(i) = xx[i]; SCR(N + i) = yy[i]; }
+            }
+        }
+    }
+    Jac<C> acc;
+    mp_copy<N>(acc.X, one);
+    mp_copy<N>(acc.Y, one);
+#pragma unroll
+    for (int i = 0; i < N; i++) acc.Z[i] = 0;
+
+#pragma unroll 1
+    for (int win = NWIN - 1; win >= 0; win--) {
+        if (win != NWIN - 1) {
+#pragma unroll 1
+            for (int k = 0; k < W; k++) pt_double<C>(acc);
+        }
+        int d = digits[(size_t)win * n + idx];
+        bool neg = d < 0, skip = d == 0;
+        int e = neg ? -d : d;          // 0..8
+        int es = e < 2 ? 2 : e;        // shared-memory slot actually read
+        uint32_t x2[N], y2[N], zc[N], zc2[N], zc3[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) {
+            uint32_t sx = TAB(es, 0, i), sy = TAB(es, 1, i);
+            uint32_t gx1 = SCR(i), gy1 = SCR(N + i);
+            x2[i] = e == 1 ? gx1 : sx;
+            y2[i] = e == 1 ? gy1 : sy;
+            zc[i] = SCR(2 * N + i); zc2[i] = SCR(3 * N + i); zc3[i] = SCR(4 * N + i);
+        }
+        pt_add_m<C, 2>(acc, x2, y2, zc, zc2, zc3, neg, skip);
+    }
+    {
+        constexpr int EU4 = 2 * N / 4;
+        uint32_t gx[N], gy[N];
+        uint32_t gb = gidx[idx];
+        load_affine<C>(gx, gy, gtab + (size_t)gb * EU4);
+#pragma unroll 1
+        for (int win = 0; win < C::GWINS; win++) {
+            uint32_t ngx[N], ngy[N];
+            uint32_t ngb = 0;
+            if (win + 1 < C::GWINS) {
+                ngb = gidx[(size_t)(win + 1) * n + idx];
+                load_affine<C>(ngx, ngy, gtab + (((size_t)(win + 1) << C::GW) + ngb) * EU4);
+            }
+            pt_add<C, true>(acc, gx, gy, one, false, gb == 0);
+            if (win + 1 < C::GWINS) { mp_copy<N>(gx, ngx); mp_copy<N>(gy, ngy); gb = ngb; }
+        }
+    }
+#undef TAB
+#undef SCR
+    bool match = false;
+    if (!mp_is_zero<N>(acc.Z)) {
+        uint32_t zz[N], r[N], rr[N], rm[N], lhs[N], pmn[N];
+        C::fsqr(zz, acc.Z);
+        load_be<N>(r, r_be + (size_t)idx * C::BYTES);
+        C::get_rr_p(rr);
+        C::fmul(rm, r, rr);
+        C::fmul(lhs, rm, zz);
+        match = mp_eq<N>(lhs, acc.X);
+        C::get_p_minus_n(pmn);
+        if (!match && mp_lt<N>(r, pmn)) {
+            uint32_t r2[N], nmod[N];
+            C::get_n(nmod);
+            mp_add<N>(r2, r, nmod);
+            C::fmul(rm, r2, rr);
+            C::fmul(lhs, rm, zz);
+            match = mp_eq<N>(lhs, acc.X);
+        }
+    }
+    ok_out[idx] = (good && match) ? 1 : 0;
+}
+
 }  // namespace sbv

@@ -45,7 +45,50 @@ int launch_verify_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const u
     return 0;
 }
 
+// co-Z 4-bit-window variant (k_verify_coz)
+template <class C, int BLOCK, int MINB>
+int launch_verify_coz_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
+                        const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st, int curve_idx) {
+    constexpr int S = 8;
+    const uint32_t nn = (uint32_t)n;
+    const uint32_t pthreads = (nn + S - 1) / S;
+    Dev::Scratch *w = nullptr;
+    if (int rc = sbv_take_scratch(e, d, st, &w)) return rc;
+    cudaEvent_t *ev = nullptr;
+    if (e->profiling) {
+        if (d.prof_used + 3 > d.prof_events.size()) {
+            size_t old = d.prof_events.size();
+            d.prof_events.resize(old + 96);
+            for (size_t i = old; i < d.prof_events.size(); i++) CU(e, cudaEventCreate(&d.prof_events[i]));
+        }
+        ev = &d.prof_events[d.prof_used];
+        d.prof_used += 3;
+        CU(e, cudaEventRecord(ev[0], st));
+    }
+    k_prep<C, 4, S><<<(pthreads + 127) / 128, 128, 0, st>>>(nn, d_r, d_s, d_dig, dlen, w->gidx, w->digits, w->flags);
+    if (ev) CU(e, cudaEventRecord(ev[1], st));
+    const size_t smem = (size_t)7 * 2 * C::N * 4 * BLOCK;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CU(e, cudaFuncSetAttribute(k_verify_coz<C, BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    k_verify_coz<C, BLOCK, MINB><<<(nn + BLOCK - 1) / BLOCK, BLOCK, smem, st>>>(
+        nn, d_qx, d_qy, d_r, w->gidx, w->digits, w->flags, reinterpret_cast<const uint4 *>(d.gtab[curve_idx]), w->tscr, d_ok);
+    if (ev) CU(e, cudaEventRecord(ev[2], st));
+    CU(e, cudaEventRecord(w->done, st));
+    e->launches += 2;
+    CU(e, cudaGetLastError());
+    return 0;
+}
+
 }  // namespace sbv
+
+#define SBV_DEFINE_LAUNCHER_COZ(NAME, CURVE, BLOCK, MINB, IDX)                                                              \
+    int NAME(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,               \
+             const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st) {                 \
+        return sbv::launch_verify_coz_t<sbv::CURVE, BLOCK, MINB>(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st, IDX); \
+    }
 
 #define SBV_DEFINE_LAUNCHER(NAME, CURVE, W, BLOCK, MINB, IDX)                                                                 \
     int NAME(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,               \
