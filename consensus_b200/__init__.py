@@ -22,7 +22,7 @@ SYMBOLS = [
     "sbv_verify_batch_device", "sbv_verify_batch_der", "sbv_sha256_batch", "sbv_hash_verify_batch",
     "sbv_verify_mixed", "sbv_quorum", "sbv_compute_quorum", "sbv_set_keys", "sbv_kernel_launches",
     "sbv_probe_mad_rate", "sbv_profile_enable", "sbv_profile_read", "sbv_verify_registered",
-    "sbv_verify_registered_device",
+    "sbv_verify_registered_device", "sbv_hash_verify_registered",
 ]
 
 
@@ -167,6 +167,18 @@ class Engine:
         ok = np.zeros(n, np.uint8)
         self._check(self._lib.sbv_verify_registered(self._h, C.c_uint8(curve), C.c_size_t(n), key_slot.ctypes.data_as(C.POINTER(C.c_uint32)),
                                                     _p8(r), _p8(s), _p8(digest), C.c_uint8(dlen), _p8(ok)), "sbv_verify_registered")
+        return ok
+
+    def hash_verify_registered(self, curve, msgs, off, key_slot, r, s) -> np.ndarray:
+        msgs = _u8(msgs if len(msgs) else np.zeros(1, np.uint8))
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        key_slot = np.ascontiguousarray(key_slot, dtype=np.uint32)
+        r, s = _u8(r), _u8(s)
+        n = off.size - 1
+        ok = np.zeros(n, np.uint8)
+        self._check(self._lib.sbv_hash_verify_registered(self._h, C.c_uint8(curve), C.c_size_t(n), _p8(msgs), off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                         key_slot.ctypes.data_as(C.POINTER(C.c_uint32)), _p8(r), _p8(s), _p8(ok)),
+                    "sbv_hash_verify_registered")
         return ok
 
     def verify_registered_device(self, curve, n, d_slot, d_r, d_s, d_digest, dlen, d_ok, stream=0, device_index=0):

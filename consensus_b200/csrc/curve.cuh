@@ -116,7 +116,13 @@ struct P256 {
     }
     SBV_DEV static void nmul(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
         const uint32_t n[8] = SBV_P256_N;
-        mont_mul_generic<8>(r, a, b, n, SBV_P256_NINV);
+        const uint32_t ni[8] = SBV_P256_NINV_FULL;
+        mont_mul_sos<8>(r, a, b, n, ni);
+    }
+    SBV_DEV static void nsqr(uint32_t (&r)[8], const uint32_t (&a)[8]) {
+        const uint32_t n[8] = SBV_P256_N;
+        const uint32_t ni[8] = SBV_P256_NINV_FULL;
+        mont_sqr_sos<8>(r, a, n, ni);
     }
 };
 
@@ -200,7 +206,13 @@ struct P384 {
     }
     SBV_DEV static void nmul(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
         const uint32_t n[12] = SBV_P384_N;
-        mont_mul_generic<12>(r, a, b, n, SBV_P384_NINV);
+        const uint32_t ni[12] = SBV_P384_NINV_FULL;
+        mont_mul_sos<12>(r, a, b, n, ni);
+    }
+    SBV_DEV static void nsqr(uint32_t (&r)[12], const uint32_t (&a)[12]) {
+        const uint32_t n[12] = SBV_P384_N;
+        const uint32_t ni[12] = SBV_P384_NINV_FULL;
+        mont_sqr_sos<12>(r, a, n, ni);
     }
 };
 
@@ -364,15 +376,30 @@ __device__ __noinline__ void f_inv(uint32_t (&r)[C::N], const uint32_t (&a)[C::N
     }
     mp_copy<N>(r, acc);
 }
-// r = a^(n-2) mod n (Montgomery form in/out, R = 2^(32N))
+// r = a^(n-2) mod n (Montgomery form in/out, R = 2^(32N)): 4-bit fixed-window exponentiation,
+// 32N squarings + at most 8N multiplications (zero nibbles are skipped) + 14 for the table.
 template <class C>
 __device__ __noinline__ void n_inv(uint32_t (&r)[C::N], const uint32_t (&a)[C::N]) {
     constexpr int N = C::N;
+    uint32_t tabn[16][N];
+    C::get_one_n(tabn[0]);
+    mp_copy<N>(tabn[1], a);
+    for (int k = 2; k < 16; k++) {
+        uint32_t t[N], u[N], v[N];
+        for (int i = 0; i < N; i++) { u[i] = tabn[k - 1][i]; v[i] = tabn[1][i]; }
+        C::nmul(t, u, v);
+        for (int i = 0; i < N; i++) tabn[k][i] = t[i];
+    }
     uint32_t acc[N];
     C::get_one_n(acc);
-    for (int i = 32 * N - 1; i >= 0; i--) {
-        C::nmul(acc, acc, acc);
-        if ((C::n_minus_2_limb(i >> 5) >> (i & 31)) & 1u) C::nmul(acc, acc, a);
+    for (int nib = 8 * N - 1; nib >= 0; nib--) {
+        if (nib != 8 * N - 1) { C::nsqr(acc, acc); C::nsqr(acc, acc); C::nsqr(acc, acc); C::nsqr(acc, acc); }
+        const uint32_t d = (C::n_minus_2_limb(nib >> 3) >> (4 * (nib & 7))) & 15u;
+        if (d) {
+            uint32_t t[N];
+            for (int i = 0; i < N; i++) t[i] = tabn[d][i];
+            C::nmul(acc, acc, t);
+        }
     }
     mp_copy<N>(r, acc);
 }

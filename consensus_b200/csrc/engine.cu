@@ -197,6 +197,31 @@ int sbv_lane_ensure(sbv_engine *e, Dev &d, Dev::Lane &ln, size_t n, size_t pinne
     (void)d;
     return 0;
 }
+int sbv_lane_ensure_msgs(sbv_engine *e, Dev::Lane &ln, size_t bytes, size_t n_off) {
+    if (bytes > ln.msg_cap) {
+        CU(e, cudaStreamSynchronize(ln.stream));
+        if (ln.d_msgs) cudaFree(ln.d_msgs);
+        ln.d_msgs = nullptr;
+        const size_t cap = bytes + bytes / 8 + 4096;
+        CU(e, cudaMalloc(&ln.d_msgs, cap));
+        ln.msg_cap = cap;
+    }
+    if (n_off > ln.off_cap) {
+        CU(e, cudaStreamSynchronize(ln.stream));
+        if (ln.d_off) cudaFree(ln.d_off);
+        ln.d_off = nullptr;
+        const size_t cap = n_off + n_off / 8 + 1024;
+        CU(e, cudaMalloc(&ln.d_off, cap * sizeof(uint64_t)));
+        ln.off_cap = cap;
+    }
+    return 0;
+}
+int sbv_launch_sha256(sbv_engine *e, size_t n, const uint8_t *d_msgs, const uint64_t *d_off, uint64_t base, uint8_t *d_digest, cudaStream_t st) {
+    k_sha256<<<(uint32_t)((n + 127) / 128), 128, 0, st>>>((uint32_t)n, d_msgs, d_off, base, d_digest);
+    e->launches += 1;
+    CU(e, cudaGetLastError());
+    return 0;
+}
 int sbv_lane_h2d(sbv_engine *e, Dev::Lane &ln, void *dst, const void *src, size_t bytes, size_t &stage_off) {
     if (bytes == 0) return 0;
     if (is_pinned(src)) {
@@ -367,7 +392,7 @@ void sbv_destroy(sbv_engine *e) {
         sbv_keys_free(d);
         for (auto &ln : d.lanes) {
             if (ln.stream) cudaStreamSynchronize(ln.stream);
-            void *lp[] = {ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, ln.d_ok, ln.d_slot};
+            void *lp[] = {ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, ln.d_ok, ln.d_slot, ln.d_msgs, ln.d_off};
             for (void *p : lp) if (p) cudaFree(p);
             if (ln.h_pin) cudaFreeHost(ln.h_pin);
             if (ln.stream) cudaStreamDestroy(ln.stream);

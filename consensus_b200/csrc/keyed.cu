@@ -160,4 +160,48 @@ int sbv_verify_registered(sbv_engine *e, uint8_t curve, size_t n, const uint32_t
     return SBV_OK;
 }
 
+// Fused SHA-256 -> registered-key verify: messages hashed on the device, digests never leave it.
+int sbv_hash_verify_registered(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *msgs, const uint64_t *msg_off,
+                               const uint32_t *key_slot, const uint8_t *r, const uint8_t *s, uint8_t *ok) {
+    if (!e || curve > SBV_P384) return sbv_fail(e, SBV_ERR_ARG, "sbv_hash_verify_registered: bad argument");
+    if (n == 0) return SBV_OK;
+    if (!msg_off || !key_slot || !r || !s || !ok || (!msgs && msg_off[n] != msg_off[0])) return sbv_fail(e, SBV_ERR_ARG, "null buffer");
+    if (n > 0x7fffffffu) return sbv_fail(e, SBV_ERR_ARG, "n too large");
+    const size_t L = curve == SBV_P256 ? 32 : 48;
+    const int G = (int)e->devs.size();
+    const int lane = sbv_lane_acquire(e);
+    struct Release { sbv_engine *e; int lane; ~Release() { sbv_lane_release(e, lane); } } release{e, lane};
+    for (int g = 0; g < G; g++) {
+        Dev &d = e->devs[g];
+        Dev::Lane &ln = d.lanes[lane];
+        const size_t lo = n * g / G, cnt = n * (g + 1) / G - lo;
+        if (cnt == 0) continue;
+        CU(e, cudaSetDevice(d.ordinal));
+        const uint64_t bytes = msg_off[lo + cnt] - msg_off[lo];
+        int rc = sbv_lane_ensure(e, d, ln, cnt, cnt * (2 * L + 5 + 8) + bytes + 16 * 256);
+        if (rc) return rc;
+        rc = sbv_lane_ensure_msgs(e, ln, bytes + 16, cnt + 1);
+        if (rc) return rc;
+        size_t so = 0;
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_msgs, msgs + msg_off[lo], bytes, so))) return rc;
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_off, msg_off + lo, (cnt + 1) * 8, so))) return rc;
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_slot, key_slot + lo, cnt * 4, so))) return rc;
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_r, r + lo * L, cnt * L, so))) return rc;
+        if ((rc = sbv_lane_h2d(e, ln, ln.d_s, s + lo * L, cnt * L, so))) return rc;
+        {
+            std::lock_guard<std::mutex> lk(e->mu);
+            rc = sbv_launch_sha256(e, cnt, ln.d_msgs, ln.d_off, msg_off[lo], ln.d_dig, ln.stream);
+            if (!rc) rc = sbv_ensure_workspace(e, d, cnt);
+            if (!rc) rc = sbv_launch_keyed(e, d, curve, cnt, ln.d_slot, ln.d_r, ln.d_s, ln.d_dig, 32, ln.d_ok, ln.stream);
+        }
+        if (rc) return rc;
+        CU(e, cudaMemcpyAsync(ok + lo, ln.d_ok, cnt, cudaMemcpyDeviceToHost, ln.stream));
+    }
+    for (int g = 0; g < G; g++) {
+        CU(e, cudaSetDevice(e->devs[g].ordinal));
+        if (e->devs[g].lanes[lane].stream) CU(e, cudaStreamSynchronize(e->devs[g].lanes[lane].stream));
+    }
+    return SBV_OK;
+}
+
 }  // extern "C"

@@ -183,6 +183,86 @@ SBV_DEV void mod_sub(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&
     r[N - 1] = addc(d[N - 1], m[N - 1] & mask);
 }
 
+// r[0..N) = (a * b) mod 2^(32N): the low half only (N(N+1)/2 wide MADs; the top product of each chain
+// spills its high word into limb N, which is discarded).
+template <int N>
+SBV_DEV void mp_mul_lo(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&b)[N]) {
+    static_assert(N % 2 == 0, "even limb count");
+    uint32_t E[N + 2], O[N + 2];  // O[k] has weight 2^(32(k+1))
+#pragma unroll
+    for (int i = 0; i < N + 2; i++) { E[i] = 0; O[i] = 0; }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        if ((j & 1) == 0) {
+            // i even -> E at limb i+j (needs i+j <= N-1) ; i odd -> O at index i+j-1
+            mad_wide_cc(E[j], E[j + 1], a[0], b[j]);
+#pragma unroll
+            for (int i = 2; i + j < N; i += 2) madc_wide_cc(E[i + j], E[i + j + 1], a[i], b[j]);
+            if (j + 1 < N) {
+                mad_wide_cc(O[j], O[j + 1], a[1], b[j]);
+#pragma unroll
+                for (int i = 3; i + j < N; i += 2) madc_wide_cc(O[i + j - 1], O[i + j], a[i], b[j]);
+            }
+        } else {
+            if (j + 1 < N) {
+                mad_wide_cc(E[j + 1], E[j + 2], a[1], b[j]);
+#pragma unroll
+                for (int i = 3; i + j < N; i += 2) madc_wide_cc(E[i + j], E[i + j + 1], a[i], b[j]);
+            }
+            mad_wide_cc(O[j - 1], O[j], a[0], b[j]);
+#pragma unroll
+            for (int i = 2; i + j < N; i += 2) madc_wide_cc(O[i + j - 1], O[i + j], a[i], b[j]);
+        }
+    }
+    r[0] = E[0];
+    r[1] = add_cc(E[1], O[0]);
+#pragma unroll
+    for (int i = 2; i < N - 1; i++) r[i] = addc_cc(E[i], O[i - 1]);
+    r[N - 1] = addc(E[N - 1], O[N - 2]);
+}
+
+// Montgomery reduction in separated-operand form: M = (T mod R) * minv_full mod R, r = (T + M*m) / R.
+// Three independent-chain products instead of a word-serial carry walk: ~2x shorter dependency
+// chain, which is what the latency-bound scalar-inversion kernel needs.  minv_full = -m^-1 mod R.
+template <int N>
+SBV_DEV void mont_reduce_sos(uint32_t (&r)[N], const uint32_t (&T)[2 * N], const uint32_t (&m)[N], const uint32_t (&minv_full)[N]) {
+    uint32_t lo[N], M[N], U[2 * N];
+#pragma unroll
+    for (int i = 0; i < N; i++) lo[i] = T[i];
+    mp_mul_lo<N>(M, lo, minv_full);
+    mp_mul<N>(U, M, m);
+    // (T + U) has zero low half; the carry out of the low half is 1 unless T_lo == 0
+    uint32_t carry_lo = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) carry_lo |= T[i];
+    carry_lo = carry_lo ? 1u : 0u;
+    uint32_t hi[N];
+    hi[0] = add_cc(T[N], carry_lo);
+#pragma unroll
+    for (int i = 1; i < N; i++) hi[i] = addc_cc(T[N + i], 0);
+    uint32_t top = addc(0, 0);
+    hi[0] = add_cc(hi[0], U[N]);
+#pragma unroll
+    for (int i = 1; i < N; i++) hi[i] = addc_cc(hi[i], U[N + i]);
+    top = addc(top, 0);
+    uint32_t t[N];
+    uint32_t bw = mp_sub<N>(t, hi, m);
+    bool use_t = (top != 0) || (bw == 0);
+    mp_select<N>(r, use_t, t, hi);
+}
+template <int N>
+SBV_DEV void mont_mul_sos(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&b)[N], const uint32_t (&m)[N], const uint32_t (&minv_full)[N]) {
+    uint32_t T[2 * N];
+    mp_mul<N>(T, a, b);
+    mont_reduce_sos<N>(r, T, m, minv_full);
+}
+template <int N>
+SBV_DEV void mont_sqr_sos(uint32_t (&r)[N], const uint32_t (&a)[N], const uint32_t (&m)[N], const uint32_t (&minv_full)[N]) {
+    uint32_t T[2 * N];
+    mp_sqr<N>(T, a);
+    mont_reduce_sos<N>(r, T, m, minv_full);
+}
+
 // Generic word-serial Montgomery reduction: r = T * 2^(-32N) mod m for T < m * 2^(32N),
 // minv = -m^-1 mod 2^32.  Used for arithmetic mod the group order n and for the P-384 field.
 template <int N>

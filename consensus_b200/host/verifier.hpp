@@ -87,7 +87,8 @@ inline bool parse_der_sig(const Bytes &sig, uint8_t r[32], uint8_t s[32]) {
 
 // One unit of work for the engine: verify (r, s) by key (X||Y) over SHA-256(message).
 struct SigItem {
-    uint8_t r[32], s[32], key[64];
+    uint8_t r[32], s[32];
+    uint32_t slot = 0;  // index into the engine's key registry (sbv_set_keys)
     Bytes message;
 };
 // Verifies a batch; returns one verdict byte per item.  Production: GpuVerifier::engine_batch.
@@ -222,26 +223,32 @@ class GpuVerifier : public IVerifier {
     }
     ~GpuVerifier() override { agg_.reset(); sbv_destroy(eng_); }
 
-    void SetConsenterKey(uint64_t id, const uint8_t xy[64]) { std::lock_guard<std::mutex> lk(mu_); memcpy(consenters_[id].data(), xy, 64); }
-    void SetClientKey(const std::string &client, const uint8_t xy[64]) { std::lock_guard<std::mutex> lk(mu_); memcpy(clients_[client].data(), xy, 64); }
+    // Keys are registered with the engine (sbv_set_keys builds a fixed-base comb table per key), so every
+    // verification below is the registered-key path.  The registry is rebuilt lazily after changes —
+    // keys change only with a reconfiguration (a new verification sequence).
+    void SetConsenterKey(uint64_t id, const uint8_t xy[64]) { std::lock_guard<std::mutex> lk(mu_); consenters_[id] = slot_of(xy); }
+    void SetClientKey(const std::string &client, const uint8_t xy[64]) { std::lock_guard<std::mutex> lk(mu_); clients_[client] = slot_of(xy); }
     void SetVerificationSequence(uint64_t v) { std::lock_guard<std::mutex> lk(mu_); verSeq_ = v; }
     Aggregator &aggregator() { return *agg_; }
     sbv_engine *engine() { return eng_; }
 
-    // One engine call: SHA-256 of every message and ECDSA-P256 verification, both on the GPU.
+    // One engine call: SHA-256 of every message and ECDSA-P256 verification against the registered
+    // keys, both on the GPU.
     std::vector<uint8_t> engine_batch(const std::vector<SigItem> &items) {
+        sync_registry();
         const size_t n = items.size();
-        std::vector<uint8_t> r(n * 32), s(n * 32), qx(n * 32), qy(n * 32), ok(n), msgs;
+        std::vector<uint8_t> r(n * 32), s(n * 32), ok(n), msgs;
+        std::vector<uint32_t> slot(n);
         std::vector<uint64_t> off(n + 1, 0);
         for (size_t i = 0; i < n; i++) {
             memcpy(&r[32 * i], items[i].r, 32); memcpy(&s[32 * i], items[i].s, 32);
-            memcpy(&qx[32 * i], items[i].key, 32); memcpy(&qy[32 * i], items[i].key + 32, 32);
+            slot[i] = items[i].slot;
             msgs.insert(msgs.end(), items[i].message.begin(), items[i].message.end());
             off[i + 1] = msgs.size();
         }
         if (msgs.empty()) msgs.push_back(0);
-        int rc = sbv_hash_verify_batch(eng_, SBV_P256, n, msgs.data(), off.data(), r.data(), s.data(), qx.data(), qy.data(), nullptr, ok.data());
-        if (rc != SBV_OK) throw EngineFault(std::string("sbv_hash_verify_batch: ") + sbv_last_error(eng_));
+        int rc = sbv_hash_verify_registered(eng_, SBV_P256, n, msgs.data(), off.data(), slot.data(), r.data(), s.data(), ok.data());
+        if (rc != SBV_OK) throw EngineFault(std::string("sbv_hash_verify_registered: ") + sbv_last_error(eng_));
         return ok;
     }
 
@@ -327,7 +334,7 @@ class GpuVerifier : public IVerifier {
             std::lock_guard<std::mutex> lk(mu_);
             auto k = consenters_.find(sig.ID);
             if (k == consenters_.end()) return Errorf("unknown consenter " + std::to_string(sig.ID));
-            memcpy(it.key, k->second.data(), 64);
+            it.slot = k->second;
         }
         if (!parse_der_sig(sig.Value, it.r, it.s)) return Errorf("malformed signature from " + std::to_string(sig.ID));
         it.message = sig.Msg;
@@ -344,19 +351,48 @@ class GpuVerifier : public IVerifier {
             std::lock_guard<std::mutex> lk(mu_);
             auto k = clients_.find(pr.client);
             if (k == clients_.end()) return Errorf("unknown client " + pr.client);
-            memcpy(it.key, k->second.data(), 64);
+            it.slot = k->second;
         }
         if (!parse_der_sig(pr.sig, it.r, it.s)) return Errorf("malformed request signature");
         it.message = pr.signedBytes;
         info = {pr.client, pr.id};
         return std::nullopt;
     }
+    uint32_t slot_of(const uint8_t xy[64]) {  // mu_ held
+        std::array<uint8_t, 64> k;
+        memcpy(k.data(), xy, 64);
+        auto f = slots_.find(k);
+        if (f != slots_.end()) return f->second;
+        uint32_t s = (uint32_t)registry_.size();
+        registry_.push_back(k);
+        slots_[k] = s;
+        dirty_ = true;
+        return s;
+    }
+    void sync_registry() {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (!dirty_) return;
+        const size_t n = registry_.size();
+        std::vector<uint64_t> ids(n);
+        std::vector<uint8_t> curve(n, SBV_P256), xy(n * 96, 0);
+        for (size_t i = 0; i < n; i++) {
+            ids[i] = i;
+            memcpy(&xy[96 * i + 16], registry_[i].data(), 32);
+            memcpy(&xy[96 * i + 48 + 16], registry_[i].data() + 32, 32);
+        }
+        if (sbv_set_keys(eng_, verSeq_, n, ids.data(), curve.data(), xy.data()) != SBV_OK)
+            throw EngineFault(std::string("sbv_set_keys: ") + sbv_last_error(eng_));
+        dirty_ = false;
+    }
     sbv_engine *eng_ = nullptr;
     std::unique_ptr<Aggregator> agg_;
     std::mutex mu_;
     uint64_t verSeq_ = 0;
-    std::map<uint64_t, std::array<uint8_t, 64>> consenters_;
-    std::map<std::string, std::array<uint8_t, 64>> clients_;
+    bool dirty_ = false;
+    std::vector<std::array<uint8_t, 64>> registry_;
+    std::map<std::array<uint8_t, 64>, uint32_t> slots_;
+    std::map<uint64_t, uint32_t> consenters_;
+    std::map<std::string, uint32_t> clients_;
 };
 
 }  // namespace sbft

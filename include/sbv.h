@@ -120,6 +120,10 @@ int sbv_set_keys(sbv_engine *e, uint64_t verification_seq, size_t n, const uint6
  * the keys-per-item entry point. */
 int sbv_verify_registered(sbv_engine *e, uint8_t curve, size_t n, const uint32_t *key_slot, const uint8_t *r,
                           const uint8_t *s, const uint8_t *digest, uint8_t digest_len, uint8_t *ok);
+/* Fused SHA-256 -> registered-key verify (VerifyConsenterSig / VerifySignature / VerifyRequest with
+ * registered consenter or client keys): messages hashed on the device. */
+int sbv_hash_verify_registered(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *msgs, const uint64_t *msg_off,
+                               const uint32_t *key_slot, const uint8_t *r, const uint8_t *s, uint8_t *ok);
 int sbv_verify_registered_device(sbv_engine *e, int device_index, uint8_t curve, size_t n, const uint32_t *d_key_slot,
                                  const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_digest, uint8_t digest_len,
                                  uint8_t *d_ok, void *cuda_stream);
