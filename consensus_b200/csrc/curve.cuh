@@ -378,17 +378,23 @@ __device__ __noinline__ void f_inv(uint32_t (&r)[C::N], const uint32_t (&a)[C::N
 }
 // r = a^(n-2) mod n (Montgomery form in/out, R = 2^(32N)): 4-bit fixed-window exponentiation,
 // 32N squarings + at most 8N multiplications (zero nibbles are skipped) + 14 for the table.
+// The 16-entry window table lives in caller-provided shared memory, word (k*N + i) of this thread at
+// tab[(k*N + i) * stride + lane] (bank = lane): per-thread local arrays of this size thrash L2 once
+// a hundred thousand threads are resident.
 template <class C>
-__device__ __noinline__ void n_inv(uint32_t (&r)[C::N], const uint32_t (&a)[C::N]) {
+__device__ __noinline__ void n_inv(uint32_t (&r)[C::N], const uint32_t (&a)[C::N], uint32_t *tab, uint32_t stride, uint32_t lane) {
     constexpr int N = C::N;
-    uint32_t tabn[16][N];
-    C::get_one_n(tabn[0]);
-    mp_copy<N>(tabn[1], a);
+#define NTAB(k, i) tab[((k) * N + (i)) * stride + lane]
+    {
+        uint32_t o[N];
+        C::get_one_n(o);
+        for (int i = 0; i < N; i++) { NTAB(0, i) = o[i]; NTAB(1, i) = a[i]; }
+    }
     for (int k = 2; k < 16; k++) {
-        uint32_t t[N], u[N], v[N];
-        for (int i = 0; i < N; i++) { u[i] = tabn[k - 1][i]; v[i] = tabn[1][i]; }
-        C::nmul(t, u, v);
-        for (int i = 0; i < N; i++) tabn[k][i] = t[i];
+        uint32_t t[N], u[N];
+        for (int i = 0; i < N; i++) u[i] = NTAB(k - 1, i);
+        C::nmul(t, u, a);
+        for (int i = 0; i < N; i++) NTAB(k, i) = t[i];
     }
     uint32_t acc[N];
     C::get_one_n(acc);
@@ -397,10 +403,11 @@ __device__ __noinline__ void n_inv(uint32_t (&r)[C::N], const uint32_t (&a)[C::N
         const uint32_t d = (C::n_minus_2_limb(nib >> 3) >> (4 * (nib & 7))) & 15u;
         if (d) {
             uint32_t t[N];
-            for (int i = 0; i < N; i++) t[i] = tabn[d][i];
+            for (int i = 0; i < N; i++) t[i] = NTAB(d, i);
             C::nmul(acc, acc, t);
         }
     }
+#undef NTAB
     mp_copy<N>(r, acc);
 }
 

@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restr
     }
     if (cnt == 0) return;
     uint32_t inv[N];
-    n_inv<C>(inv, run);
+    extern __shared__ uint32_t ninv_tab[];  // 16 * N words per thread, bank = lane
+    n_inv<C>(inv, run, ninv_tab, blockDim.x, threadIdx.x);
     for (int k = cnt - 1; k >= 0; k--) {
         uint32_t idx = t + (uint32_t)k * T;
         uint32_t w[N], m[N];
@@ -180,6 +181,23 @@ __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restr
             digits[(size_t)i * n + idx] = (int8_t)(sign ? -(int)d : (int)d);
         }
     }
+}
+
+// host-side launcher of k_prep (dynamic shared memory = the inversion window table of each thread)
+template <class C, int W, int S>
+inline cudaError_t launch_prep(uint32_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_dig, uint32_t dlen, uint16_t *gidx,
+                               int8_t *digits, uint8_t *flags, cudaStream_t st) {
+    constexpr int PB = 128;
+    const size_t smem = (size_t)16 * C::N * 4 * PB;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t rc = cudaFuncSetAttribute(k_prep<C, W, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (rc != cudaSuccess) return rc;
+        attr_done = true;
+    }
+    const uint32_t pthreads = (n + S - 1) / S;
+    k_prep<C, W, S><<<(pthreads + PB - 1) / PB, PB, smem, st>>>(n, d_r, d_s, d_dig, dlen, gidx, digits, flags);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -67,7 +67,6 @@ static int launch_keyed_t(sbv_engine *e, Dev &d, int c, size_t n, const uint32_t
                           const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st) {
     constexpr int S = 8, BLOCK = 128;
     const uint32_t nn = (uint32_t)n;
-    const uint32_t pthreads = (nn + S - 1) / S;
     Dev::Scratch *w = nullptr;
     if (int rc = sbv_take_scratch(e, d, st, &w)) return rc;
     cudaEvent_t *ev = nullptr;
@@ -81,7 +80,7 @@ static int launch_keyed_t(sbv_engine *e, Dev &d, int c, size_t n, const uint32_t
         d.prof_used += 3;
         CU(e, cudaEventRecord(ev[0], st));
     }
-    k_prep<C, 0, S><<<(pthreads + 127) / 128, 128, 0, st>>>(nn, d_r, d_s, d_dig, dlen, w->gidx, w->digits, w->flags);
+    CU(e, (launch_prep<C, 0, S>(nn, d_r, d_s, d_dig, dlen, w->gidx, w->digits, w->flags, st)));
     if (ev) CU(e, cudaEventRecord(ev[1], st));
     k_verify_keyed<C, BLOCK><<<(nn + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(
         nn, d_slot, d.slot2local[c], d.n_slots, d.keyflags[c], d_r, w->gidx, reinterpret_cast<const uint8_t *>(w->digits), w->flags,

@@ -12,8 +12,6 @@ int launch_verify_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const u
     constexpr int S = 8;
     constexpr int TE = Windows<32 * C::N, W>::ENTRIES;
     const uint32_t nn = (uint32_t)n;
-    const uint32_t pthreads = (nn + S - 1) / S;
-    const uint32_t pblocks = (pthreads + 127) / 128;
     Dev::Scratch *w = nullptr;
     if (int rc = sbv_take_scratch(e, d, st, &w)) return rc;
     cudaEvent_t *ev = nullptr;
@@ -27,7 +25,7 @@ int launch_verify_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const u
         d.prof_used += 3;
         CU(e, cudaEventRecord(ev[0], st));
     }
-    k_prep<C, W, S><<<pblocks, 128, 0, st>>>(nn, d_r, d_s, d_dig, dlen, w->gidx, w->digits, w->flags);
+    CU(e, (launch_prep<C, W, S>(nn, d_r, d_s, d_dig, dlen, w->gidx, w->digits, w->flags, st)));
     if (ev) CU(e, cudaEventRecord(ev[1], st));
     const size_t smem = (size_t)TE * 3 * C::N * 4 * BLOCK;
     static bool attr_done = false;
@@ -51,7 +49,6 @@ int launch_verify_coz_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, con
                         const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st, int curve_idx) {
     constexpr int S = 8;
     const uint32_t nn = (uint32_t)n;
-    const uint32_t pthreads = (nn + S - 1) / S;
     Dev::Scratch *w = nullptr;
     if (int rc = sbv_take_scratch(e, d, st, &w)) return rc;
     cudaEvent_t *ev = nullptr;
@@ -65,7 +62,7 @@ int launch_verify_coz_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, con
         d.prof_used += 3;
         CU(e, cudaEventRecord(ev[0], st));
     }
-    k_prep<C, 4, S><<<(pthreads + 127) / 128, 128, 0, st>>>(nn, d_r, d_s, d_dig, dlen, w->gidx, w->digits, w->flags);
+    CU(e, (launch_prep<C, 4, S>(nn, d_r, d_s, d_dig, dlen, w->gidx, w->digits, w->flags, st)));
     if (ev) CU(e, cudaEventRecord(ev[1], st));
     const size_t smem = (size_t)7 * 2 * C::N * 4 * BLOCK;
     static bool attr_done = false;
