@@ -351,6 +351,7 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
     if (cudaGetDeviceCount(&count) != cudaSuccess || count < n_devices) return SBV_ERR_CUDA;
     sbv_engine *e = new sbv_engine();
     e->p256_variant = env_int("SBV_P256_VARIANT", 1);
+    e->keyed_warp_limit = env_int("SBV_KEYED_WARP_LIMIT", 2048);
     e->devs.resize(n_devices);
     for (int g = 0; g < n_devices; g++) {
         Dev &d = e->devs[g];

@@ -72,6 +72,7 @@ struct sbv_engine {
     bool lane_busy[2] = {false, false};
     std::string err;
     uint64_t launches = 0;
+    int keyed_warp_limit = 2048;  // registered-key batches up to this size use one warp per signature (SBV_KEYED_WARP_LIMIT)
     int p256_variant = 1;  // 1 = co-Z 4-bit window (default), 0 = 3-bit Jacobian window (SBV_P256_VARIANT=0)
     bool profiling = false;
     // NCCL (multi-device only; loaded lazily with dlopen so single-device users never touch it)

@@ -82,6 +82,12 @@ static int launch_keyed_t(sbv_engine *e, Dev &d, int c, size_t n, const uint32_t
     }
     CU(e, (launch_prep<C, 0, S>(nn, d_r, d_s, d_dig, dlen, w->gidx, w->digits, w->flags, st)));
     if (ev) CU(e, cudaEventRecord(ev[1], st));
+    const uint32_t warp_limit = (uint32_t)e->keyed_warp_limit;
+    if (nn <= warp_limit)  // small batch: one signature per warp (latency path)
+        k_verify_keyed_warp<C><<<(nn * 32 + 127) / 128, 128, 0, st>>>(
+            nn, d_slot, d.slot2local[c], d.n_slots, d.keyflags[c], d_r, w->gidx, reinterpret_cast<const uint8_t *>(w->digits), w->flags,
+            reinterpret_cast<const uint4 *>(d.gtab[c]), reinterpret_cast<const uint4 *>(d.ktab[c]), d_ok);
+    else
     k_verify_keyed<C, BLOCK><<<(nn + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(
         nn, d_slot, d.slot2local[c], d.n_slots, d.keyflags[c], d_r, w->gidx, reinterpret_cast<const uint8_t *>(w->digits), w->flags,
         reinterpret_cast<const uint4 *>(d.gtab[c]), reinterpret_cast<const uint4 *>(d.ktab[c]), d_ok);

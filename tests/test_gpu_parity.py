@@ -267,6 +267,10 @@ def test_registered_key_path_bit_exact(eng, curve):
     sel = ~np.isin(np.arange(n) % 16, [5, 6, 7])
     generic = eng.verify_batch(curve, r[sel], s[sel], qx[sel], qy[sel], dig[sel])
     assert (generic == got[sel]).all()
+    # small batches take the one-signature-per-warp kernel: same verdicts, item by item
+    for lo, cnt in [(0, 1), (1, 2), (16, 77), (100, 1000), (33, 2048)]:
+        sl = slice(lo, lo + cnt)
+        assert (eng.verify_registered(curve, slot[sl], r[sl], s[sl], dig[sl]) == want[sl]).all(), (lo, cnt)
     eng.set_keys(np.zeros(0, np.uint8), np.zeros((0, 96), np.uint8))      # empty registry: everything rejects
     assert eng.verify_registered(curve, slot[:50], r[:50], s[:50], dig[:50]).sum() == 0
 

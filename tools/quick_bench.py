@@ -58,3 +58,18 @@ c.record(); torch.cuda.synchronize()
 res["registered_16keys"] = {"ms": a.elapsed_time(c) / 10, "Mverif_s": n / (a.elapsed_time(c) / 10) / 1e3}
 e.close()
 print(json.dumps(res, indent=1))
+# ---- small-batch latency of the registered-key path: warp-per-signature vs thread-per-signature ----
+lat = {}
+for limit in (2048, 0):
+    os.environ["SBV_KEYED_WARP_LIMIT"] = str(limit)
+    e = sbv.Engine(n_devices=1)
+    e.set_keys(np.zeros(16, np.uint8), b["keys"].reshape(1024, 2, 32)[:16])
+    for m in (1, 16, 128, 1024, 2048):
+        sl = (b["key_idx"][:m] % 16).astype(np.uint32)
+        f = lambda: e.verify_registered(P256, sl, b["r"][:m], b["s"][:m], b["digest"][:m])
+        for _ in range(5): f()
+        t0 = time.perf_counter()
+        for _ in range(50): f()
+        lat[f"limit{limit}_n{m}_us"] = (time.perf_counter() - t0) / 50 * 1e6
+    e.close()
+print(json.dumps(lat, indent=1))
