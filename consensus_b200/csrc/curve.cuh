@@ -163,13 +163,58 @@ struct P384 {
     SBV_DEV static uint32_t p_minus_2_limb(int i) { const uint32_t c[12] = SBV_P384_P_MINUS_2; return c[i]; }
     SBV_DEV static uint32_t n_minus_2_limb(int i) { const uint32_t c[12] = SBV_P384_N_MINUS_2; return c[i]; }
 
-    SBV_DEV static void fmul_inline(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
+    // p = 2^384 - 2^128 - 2^96 + 2^32 - 1 and -p^-1 mod 2^64 = 2^32 + 1, so the quotient digit of a
+    // 64-bit Montgomery step is (t0, t0 + t1) and q*p = q*2^384 - q*2^128 - q*2^96 + q*2^32 - q is shifted
+    // adds: no multiplications in the reduction (one add chain, two subtract chains per step).
+    SBV_DEV static void redc(uint32_t (&r)[12], uint32_t (&T)[24]) {
+        uint32_t t24 = 0;
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            const int b = 2 * k;
+            const uint32_t mlo = T[b], mhi = T[b] + T[b + 1];
+            // + q*2^32 and + q*2^384
+            T[b + 1] = add_cc(T[b + 1], mlo);
+            T[b + 2] = addc_cc(T[b + 2], mhi);
+#pragma unroll
+            for (int j = b + 3; j < b + 12; j++) T[j] = addc_cc(T[j], 0);
+            T[b + 12] = addc_cc(T[b + 12], mlo);
+            T[b + 13] = addc_cc(T[b + 13], mhi);
+#pragma unroll
+            for (int j = b + 14; j < 24; j++) T[j] = addc_cc(T[j], 0);
+            t24 = addc(t24, 0);
+            // - q and - q*2^96
+            T[b] = sub_cc(T[b], mlo);
+            T[b + 1] = subc_cc(T[b + 1], mhi);
+            T[b + 2] = subc_cc(T[b + 2], 0);
+            T[b + 3] = subc_cc(T[b + 3], mlo);
+            T[b + 4] = subc_cc(T[b + 4], mhi);
+#pragma unroll
+            for (int j = b + 5; j < 24; j++) T[j] = subc_cc(T[j], 0);
+            t24 = subc(t24, 0);
+            // - q*2^128
+            T[b + 4] = sub_cc(T[b + 4], mlo);
+            T[b + 5] = subc_cc(T[b + 5], mhi);
+#pragma unroll
+            for (int j = b + 6; j < 24; j++) T[j] = subc_cc(T[j], 0);
+            t24 = subc(t24, 0);
+        }
+        uint32_t hi[12], t[12];
+#pragma unroll
+        for (int i = 0; i < 12; i++) hi[i] = T[12 + i];
         const uint32_t p[12] = SBV_P384_P;
-        mont_mul_generic<12>(r, a, b, p, SBV_P384_PINV);
+        uint32_t bw = mp_sub<12>(t, hi, p);
+        bool use_t = (t24 != 0) || (bw == 0);
+        mp_select<12>(r, use_t, t, hi);
+    }
+    SBV_DEV static void fmul_inline(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
+        uint32_t T[24];
+        mp_mul<12>(T, a, b);
+        redc(r, T);
     }
     SBV_DEV static void fsqr_inline(uint32_t (&r)[12], const uint32_t (&a)[12]) {
-        const uint32_t p[12] = SBV_P384_P;
-        mont_sqr_generic<12>(r, a, p, SBV_P384_PINV);
+        uint32_t T[24];
+        mp_sqr<12>(T, a);
+        redc(r, T);
     }
     // out of line, operands in registers — same reason as P256::fmul
     SBV_DEV static void fmul(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
