@@ -95,6 +95,27 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the newest
+    committed `ncu --set full` summary under profiles/ (None if there is none)."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_k_verify_ncu.txt"))):
+        tot = 0.0
+        found = 0
+        for line in open(path):
+            m = re.match(r"dram__bytes_(read|write)\.sum\s+([0-9.]+)\s+(\w+)", line)
+            if m:
+                scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(m.group(3), None)
+                if scale:
+                    tot += float(m.group(2)) * scale
+                    found += 1
+        if found == 2:
+            best = (tot, os.path.basename(path))
+    return best
+
+
 def make_workload(rank: int):
     import oracle  # corpus generator + CPU baseline live in the oracle package (test/bench infrastructure)
     from oracle import corpus
@@ -343,7 +364,9 @@ def main():
         "bound": "int32-mad (IMAD.WIDE issue rate; neither hbm nor tensor binds this path)",
         "kernel": "k_verify<P256>", "achieved": mac_rate / 1e12, "peak": mad_peak / 1e12, "unit": "TMAC32/s",
         "frac": mac_rate / mad_peak if mad_peak else None, "peak_source": "sbv_probe_mad_rate, same run",
-        "kernel_ms": k_ms, "prep_kernel_ms": prep_ms / max(pairs, 1), "traffic": None,
+        "kernel_ms": k_ms, "prep_kernel_ms": prep_ms / max(pairs, 1),
+        "traffic": (ncu_traffic_bytes() or (None, None))[0], "traffic_source": (ncu_traffic_bytes() or (None, None))[1],
+        "algorithmic_bytes_per_launch": BATCH * BYTES_PER_VERIFY,
         "hbm": {"achieved": BATCH * BYTES_PER_VERIFY / (k_ms * 1e-3) / 1e9, "peak": hbm_gbs, "unit": "GB/s",
                 "frac": BATCH * BYTES_PER_VERIFY / (k_ms * 1e-3) / 1e9 / hbm_gbs, "peak_source": hbm_src},
     }
