@@ -191,12 +191,13 @@ def main():
     pow2 = (2 ** torch.arange(8, device=dev, dtype=torch.int32)).to(torch.uint8)
     gathered = torch.zeros(world * BATCH // 8, dtype=torch.uint8, device=dev) if world > 1 else None
     stream = torch.cuda.current_stream().cuda_stream
-    # Consecutive steps are independent batches, so they are enqueued alternately on two streams: the
+    # Consecutive steps are independent batches, so they are enqueued round-robin on three streams: the
     # scalar-preparation kernel of step i+1 (latency-bound: one inversion chain) and the head of its
     # verify kernel overlap the draining tail of step i.  Every step still does all of its work; the
     # timed region is bracketed by events on the main stream that wait for both.
-    lanes = [torch.cuda.Stream(device=dev) for _ in range(2)]
-    d_oks = [torch.zeros(BATCH, dtype=torch.uint8, device=dev) for _ in range(2)]
+    N_LANES = 3
+    lanes = [torch.cuda.Stream(device=dev) for _ in range(N_LANES)]
+    d_oks = [torch.zeros(BATCH, dtype=torch.uint8, device=dev) for _ in range(N_LANES)]
 
     def device_step(i, pipelined=True):
         c = copies[i % N_COPIES]
@@ -204,8 +205,8 @@ def main():
             eng.verify_batch_device(sbv.P256, BATCH, c["r"].data_ptr(), c["s"].data_ptr(), c["qx"].data_ptr(), c["qy"].data_ptr(),
                                     c["digest"].data_ptr(), 32, d_ok.data_ptr(), stream=stream)
             return
-        lane = lanes[i % 2]
-        out = d_oks[i % 2]
+        lane = lanes[i % N_LANES]
+        out = d_oks[i % N_LANES]
         with torch.cuda.stream(lane):
             eng.verify_batch_device(sbv.P256, BATCH, c["r"].data_ptr(), c["s"].data_ptr(), c["qx"].data_ptr(), c["qy"].data_ptr(),
                                     c["digest"].data_ptr(), 32, out.data_ptr(), stream=lane.cuda_stream)
@@ -258,7 +259,7 @@ def main():
     e1.record()
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    for k in range(2):
+    for k in range(N_LANES):
         if not np.array_equal(d_oks[k].cpu().numpy(), want):
             raise SystemExit("bench: pipelined verdicts differ from the oracle")
     # single-stream steps (no overlap): step latency, and the per-kernel CUDA-event durations the
@@ -377,7 +378,7 @@ def main():
         "dtype": "u32 limbs (integer)", "data": "synthetic",
         "config": {"workload": "C2: ECDSA-P256 batch verify, 65,536 synthetic sigs per GPU, 1,024 keys, 1/16 corrupted",
                    "batch_per_gpu": BATCH, "l2": f"{N_COPIES} rotating input copies (168 MB > 126 MB L2)",
-                   "pipelining": "consecutive steps alternate over 2 CUDA streams; unpipelined step latency in step_latency_ms",
+                   "pipelining": "consecutive steps rotate over 3 CUDA streams; unpipelined step latency in step_latency_ms",
                    "exchange": "NCCL all_gather of the packed verdict bitmask per step" if world > 1 else "none (1 GPU)",
                    "sharding": f"batch-parallel x{world}"},
         "e2e": {"value": e2e_value, "unit": "verifies/s", "h2d_bytes_per_step": 160 * BATCH * world, "d2h_bytes_per_step": BATCH * world,

@@ -61,13 +61,26 @@ struct P256 {
             for (int j = b + 9; j < 16; j++) T[j] = subc_cc(T[j], 0);
             t16 = subc(t16, 0);
         }
-        uint32_t hi[8], t[8];
+        // result = hi + t16*2^256 < 2p: subtract p iff t16 or hi >= p.  p = (F,1,0,0,0,F,F,F) from the top
+        // limb down, so hi >= p is a few logic ops, and the subtraction is one chain with a masked p
+        // (no trial subtraction + select).
+        uint32_t hi[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) hi[i] = T[8 + i];
-        const uint32_t p[8] = SBV_P256_P;
-        uint32_t bw = mp_sub<8>(t, hi, p);
-        bool use_t = (t16 != 0) || (bw == 0);
-        mp_select<8>(r, use_t, t, hi);
+        const uint32_t mid = hi[3] | hi[4] | hi[5];
+        const uint32_t low = hi[0] & hi[1] & hi[2];
+        // bitwise on 0/1 values: short-circuit && / || would compile to divergent branches
+        const uint32_t ge = (uint32_t)(hi[7] == 0xffffffffu) &
+                            ((uint32_t)(hi[6] > 1u) | ((uint32_t)(hi[6] == 1u) & ((uint32_t)(mid != 0u) | (uint32_t)(low == 0xffffffffu))));
+        const uint32_t mask = 0u - ((uint32_t)(t16 != 0) | ge);
+        r[0] = sub_cc(hi[0], mask);
+        r[1] = subc_cc(hi[1], mask);
+        r[2] = subc_cc(hi[2], mask);
+        r[3] = subc_cc(hi[3], 0);
+        r[4] = subc_cc(hi[4], 0);
+        r[5] = subc_cc(hi[5], 0);
+        r[6] = subc_cc(hi[6], mask & 1u);
+        r[7] = subc(hi[7], mask);
     }
     SBV_DEV static void fmul_inline(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
         uint32_t T[16];

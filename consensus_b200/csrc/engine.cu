@@ -234,7 +234,7 @@ int sbv_lane_h2d(sbv_engine *e, Dev::Lane &ln, void *dst, const void *src, size_
     return 0;
 }
 int sbv_take_scratch(sbv_engine *e, Dev &d, cudaStream_t st, Dev::Scratch **out) {
-    Dev::Scratch &w = d.ws[d.ws_next++ & 1];
+    Dev::Scratch &w = d.ws[d.ws_next++ & 3];
     if (w.used) CU(e, cudaStreamWaitEvent(st, w.done, 0));
     w.used = true;
     *out = &w;
@@ -386,9 +386,12 @@ void sbv_destroy(sbv_engine *e) {
     for (Dev &d : e->devs) {
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        void *ptrs[] = {d.gtab[0], d.gtab[1], d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, d.d_ok, d.ws[0].gidx, d.ws[0].flags, d.ws[0].digits, d.ws[0].tscr, d.ws[1].tscr,
-                        d.ws[1].gidx, d.ws[1].flags, d.ws[1].digits, d.d_msgs, d.d_off, d.d_scratch};
-        for (auto &w : d.ws) if (w.done) cudaEventDestroy(w.done);
+        void *ptrs[] = {d.gtab[0], d.gtab[1], d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, d.d_ok,  d.d_msgs, d.d_off, d.d_scratch};
+        for (auto &w : d.ws) {
+            void *wp[] = {w.gidx, w.flags, w.digits, w.tscr};
+            for (void *p : wp) if (p) cudaFree(p);
+            if (w.done) cudaEventDestroy(w.done);
+        }
         for (void *p : ptrs) if (p) cudaFree(p);
         sbv_keys_free(d);
         for (auto &ln : d.lanes) {

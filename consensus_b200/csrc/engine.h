@@ -28,7 +28,7 @@ struct Dev {
         uint32_t *tscr = nullptr;  // k_verify_coz per-signature scratch: 12N words, word-major
         cudaEvent_t done = nullptr;
         bool used = false;
-    } ws[2];
+    } ws[4];
     unsigned ws_next = 0;
     // per-call lanes of the host-buffer entry points: own stream, input/verdict buffers and pinned staging, so
     // two host threads can have a call in flight each (H2D / kernels / D2H of one overlap the other's)
@@ -58,8 +58,6 @@ struct Dev {
     uint8_t *keyflags[2] = {nullptr, nullptr};
     int32_t *slot2local[2] = {nullptr, nullptr};
     uint32_t n_slots = 0, n_local[2] = {0, 0};
-    uint32_t *d_slot = nullptr;
-    size_t slot_cap = 0;
     // profiling: event pairs around the prep / verify kernels (only when enabled)
     std::vector<cudaEvent_t> prof_events;  // triples: before prep, between, after verify
     size_t prof_used = 0;

@@ -15,8 +15,7 @@ void sbv_keys_free(Dev &d) {
         if (d.slot2local[c]) cudaFree(d.slot2local[c]);
         d.ktab[c] = nullptr; d.keyflags[c] = nullptr; d.slot2local[c] = nullptr; d.n_local[c] = 0;
     }
-    if (d.d_slot) cudaFree(d.d_slot);
-    d.d_slot = nullptr; d.slot_cap = 0; d.n_slots = 0;
+    d.n_slots = 0;
 }
 
 int sbv_keys_build(sbv_engine *e, Dev &d) {

@@ -82,7 +82,6 @@ SBV_DEV void mp_sqr(uint32_t (&r)[2 * N], const uint32_t (&a)[N]) {
 #pragma unroll
             for (int j = i + 4; j < N; j += 2) madc_wide_cc(E[i + j], E[i + j + 1], a[i], a[j]);
             // last j of this row: N-2 or N-1 (same parity as i)
-            constexpr int dummy = 0; (void)dummy;
             const int jl = ((N - 1 - i) % 2 == 0) ? N - 1 : N - 2;
             if (i + jl + 2 < 2 * N) E[i + jl + 2] = addc(E[i + jl + 2], 0);
         }

@@ -58,6 +58,18 @@ c.record(); torch.cuda.synchronize()
 res["registered_16keys"] = {"ms": a.elapsed_time(c) / 10, "Mverif_s": n / (a.elapsed_time(c) / 10) / 1e3}
 e.close()
 print(json.dumps(res, indent=1))
+# ---- A/B at full batch: one signature per warp vs one per thread (registered-key path, 64K) ----
+for limit in (100000, 0):
+    os.environ["SBV_KEYED_WARP_LIMIT"] = str(limit)
+    e = sbv.Engine(n_devices=1)
+    e.set_keys(np.zeros(16, np.uint8), b["keys"].reshape(1024, 2, 32)[:16])
+    runk = lambda: e.verify_registered_device(P256, n, slot16.data_ptr(), t["r"].data_ptr(), t["s"].data_ptr(), t["digest"].data_ptr(), 32, ok.data_ptr(), stream=st)
+    for _ in range(3): runk()
+    a.record()
+    for _ in range(5): runk()
+    c.record(); torch.cuda.synchronize()
+    print(json.dumps({("warp_per_signature" if limit else "thread_per_signature") + "_64k_16keys_Mverif_s": n / (a.elapsed_time(c) / 5) / 1e3}))
+    e.close()
 # ---- small-batch latency of the registered-key path: warp-per-signature vs thread-per-signature ----
 lat = {}
 for limit in (2048, 0):
