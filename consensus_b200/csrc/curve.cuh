@@ -34,6 +34,7 @@ struct P256 {
     SBV_DEV static void get_gy(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_GY_MONT; mp_copy<8>(r, c); }
     SBV_DEV static void get_rr_n(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_RR_N; mp_copy<8>(r, c); }
     SBV_DEV static void get_one_n(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_ONE_N; mp_copy<8>(r, c); }
+    SBV_DEV static void get_rrr_n(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_RRR_N; mp_copy<8>(r, c); }
     SBV_DEV static void get_p_minus_n(uint32_t (&r)[8]) { const uint32_t c[8] = SBV_P256_P_MINUS_N; mp_copy<8>(r, c); }
     SBV_DEV static uint32_t p_minus_2_limb(int i) { const uint32_t c[8] = SBV_P256_P_MINUS_2; return c[i]; }
     SBV_DEV static uint32_t n_minus_2_limb(int i) { const uint32_t c[8] = SBV_P256_N_MINUS_2; return c[i]; }
@@ -172,6 +173,8 @@ struct P384 {
     SBV_DEV static void get_gy(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_GY_MONT; mp_copy<12>(r, c); }
     SBV_DEV static void get_rr_n(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_RR_N; mp_copy<12>(r, c); }
     SBV_DEV static void get_one_n(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_ONE_N; mp_copy<12>(r, c); }
+    SBV_DEV static void get_rrr_n(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_RRR_N; mp_copy<12>(r, c); }
+    static constexpr uint32_t NINV = SBV_P384_NINV;
     SBV_DEV static void get_p_minus_n(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_P_MINUS_N; mp_copy<12>(r, c); }
     SBV_DEV static uint32_t p_minus_2_limb(int i) { const uint32_t c[12] = SBV_P384_P_MINUS_2; return c[i]; }
     SBV_DEV static uint32_t n_minus_2_limb(int i) { const uint32_t c[12] = SBV_P384_N_MINUS_2; return c[i]; }
@@ -434,39 +437,71 @@ __device__ __noinline__ void f_inv(uint32_t (&r)[C::N], const uint32_t (&a)[C::N
     }
     mp_copy<N>(r, acc);
 }
-// r = a^(n-2) mod n (Montgomery form in/out, R = 2^(32N)): 4-bit fixed-window exponentiation,
-// 32N squarings + at most 8N multiplications (zero nibbles are skipped) + 14 for the table.
-// The 16-entry window table lives in caller-provided shared memory, word (k*N + i) of this thread at
-// tab[(k*N + i) * stride + lane] (bank = lane): per-thread local arrays of this size thrash L2 once
-// a hundred thousand threads are resident.
+// r = a^-1 mod n for Montgomery-form a (= A*R), result in Montgomery form (A^-1 * R).
+// Binary extended GCD on the plain residue with batched trailing-zero stripping:
+//   invariants  x1 * a == u,  x2 * a == v  (mod n), u and v odd;  each pass replaces the larger of
+//   (u, v) by |u - v| (even), strips its tz <= 31 trailing zeros and fixes the cofactor with one
+//   multiply-accumulate:  x = (x + k*n) >> tz,  k = x * (-n^-1) mod 2^tz.
+// ~0.7 passes per bit of ~150 cheap instructions — about 4x fewer (and cheaper) instructions than the
+// 4-bit-window Fermat chain, which is what the latency-bound scalar-preparation kernel needs.
+// gcd(a, n) = 1 always holds here (n prime, a != 0); the pass count is capped defensively.
 template <class C>
-__device__ __noinline__ void n_inv(uint32_t (&r)[C::N], const uint32_t (&a)[C::N], uint32_t *tab, uint32_t stride, uint32_t lane) {
+__device__ __noinline__ void n_inv(uint32_t (&r)[C::N], const uint32_t (&a)[C::N]) {
     constexpr int N = C::N;
-#define NTAB(k, i) tab[((k) * N + (i)) * stride + lane]
-    {
-        uint32_t o[N];
-        C::get_one_n(o);
-        for (int i = 0; i < N; i++) { NTAB(0, i) = o[i]; NTAB(1, i) = a[i]; }
-    }
-    for (int k = 2; k < 16; k++) {
-        uint32_t t[N], u[N];
-        for (int i = 0; i < N; i++) u[i] = NTAB(k - 1, i);
-        C::nmul(t, u, a);
-        for (int i = 0; i < N; i++) NTAB(k, i) = t[i];
-    }
-    uint32_t acc[N];
-    C::get_one_n(acc);
-    for (int nib = 8 * N - 1; nib >= 0; nib--) {
-        if (nib != 8 * N - 1) { C::nsqr(acc, acc); C::nsqr(acc, acc); C::nsqr(acc, acc); C::nsqr(acc, acc); }
-        const uint32_t d = (C::n_minus_2_limb(nib >> 3) >> (4 * (nib & 7))) & 15u;
-        if (d) {
-            uint32_t t[N];
-            for (int i = 0; i < N; i++) t[i] = NTAB(d, i);
-            C::nmul(acc, acc, t);
+    uint32_t M[N];
+    C::get_n(M);
+    uint32_t u[N], v[N], x1[N], x2[N];
+    mp_copy<N>(u, a);
+    mp_copy<N>(v, M);
+#pragma unroll
+    for (int i = 0; i < N; i++) { x1[i] = (i == 0); x2[i] = 0; }
+    // strip(t, x): t even and non-zero -> odd, cofactor adjusted
+    auto strip = [&](uint32_t (&t)[N], uint32_t (&x)[N]) {
+        while ((t[0] & 1u) == 0u) {
+            const uint32_t tz = t[0] ? (uint32_t)(__ffs((int)t[0]) - 1) : 31u;  // 1..31
+#pragma unroll
+            for (int i = 0; i < N - 1; i++) t[i] = __funnelshift_r(t[i], t[i + 1], tz);
+            t[N - 1] >>= tz;
+            const uint32_t k = (x[0] * C::NINV) & ((1u << tz) - 1u);
+            // x = (x + k*M) >> tz   (x + k*M < 2^tz * 2M fits N+1 limbs)
+            uint32_t w[N + 1];
+            uint64_t cy = 0;
+#pragma unroll
+            for (int i = 0; i < N; i++) {
+                cy += (uint64_t)k * M[i] + x[i];
+                w[i] = (uint32_t)cy;
+                cy >>= 32;
+            }
+            w[N] = (uint32_t)cy;
+#pragma unroll
+            for (int i = 0; i < N; i++) x[i] = __funnelshift_r(w[i], w[i + 1], tz);
+            uint32_t d[N];
+            const uint32_t bw = mp_sub<N>(d, x, M);   // x < 2M: one conditional subtraction
+            mp_select<N>(x, bw == 0, d, x);
         }
+    };
+    if ((u[0] & 1u) == 0u) strip(u, x1);
+    for (int pass = 0; pass < 64 * N + 8; pass++) {
+        if (mp_eq<N>(u, v)) break;
+        uint32_t d[N], xd[N], t[N];
+        const uint32_t lt = mp_sub<N>(d, u, v);        // borrow: u < v
+        if (lt) {                                       // d = v - u
+            uint32_t z[N];
+#pragma unroll
+            for (int i = 0; i < N; i++) z[i] = 0;
+            mp_sub<N>(t, z, d);
+            mp_copy<N>(d, t);
+        }
+        mod_sub<N>(xd, x1, x2, M);                      // x1 - x2 mod n (non-zero: u != v)
+        if (lt) { mp_sub<N>(t, M, xd); mp_copy<N>(xd, t); }  // x2 - x1
+        strip(d, xd);
+        if (lt) { mp_copy<N>(v, d); mp_copy<N>(x2, xd); }
+        else    { mp_copy<N>(u, d); mp_copy<N>(x1, xd); }
     }
-#undef NTAB
-    mp_copy<N>(r, acc);
+    // u == v == 1: x1 = (A*R)^-1 ; times R^3 / R -> A^-1 * R
+    uint32_t rrr[N];
+    C::get_rrr_n(rrr);
+    C::nmul(r, x1, rrr);
 }
 
 // big-endian byte string (C::BYTES, 4-byte aligned) -> little-endian limbs

@@ -19,7 +19,7 @@ __global__ void k_debug_op(int op, uint32_t n, const uint32_t *__restrict__ a, c
     else if (op == 2) C::fsub(r0, x, u);
     else if (op == 3) C::nmul(r0, x, u);
     else if (op == 4) f_inv<C>(r0, x);
-    else if (op == 8) { extern __shared__ uint32_t ninv_tab[]; n_inv<C>(r0, x, ninv_tab, blockDim.x, threadIdx.x); }
+    else if (op == 8) n_inv<C>(r0, x);
     else if (op == 9) C::fsqr(r0, x);
     else if (op >= 5 && op <= 7) {
         // affine plain (x,y) [+ (u,v)] -> Montgomery Jacobian -> op -> affine plain
@@ -61,8 +61,8 @@ extern "C" int sbv_debug_op(sbv_engine *e, uint8_t curve, int op, size_t n, cons
     uint32_t *da = (uint32_t *)d.d_scratch, *db = da + n * 2 * N, *dout = db + n * 2 * N;
     CU(e, cudaMemcpyAsync(da, a, bytes, cudaMemcpyHostToDevice, d.stream));
     CU(e, cudaMemcpyAsync(db, b, bytes, cudaMemcpyHostToDevice, d.stream));
-    if (curve == SBV_P256) k_debug_op<P256><<<(uint32_t)((n + 63) / 64), 64, 16 * 8 * 4 * 64, d.stream>>>(op, (uint32_t)n, da, db, dout);
-    else k_debug_op<P384><<<(uint32_t)((n + 63) / 64), 64, 16 * 12 * 4 * 64, d.stream>>>(op, (uint32_t)n, da, db, dout);
+    if (curve == SBV_P256) k_debug_op<P256><<<(uint32_t)((n + 63) / 64), 64, 0, d.stream>>>(op, (uint32_t)n, da, db, dout);
+    else k_debug_op<P384><<<(uint32_t)((n + 63) / 64), 64, 0, d.stream>>>(op, (uint32_t)n, da, db, dout);
     CU(e, cudaGetLastError());
     CU(e, cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, d.stream));
     CU(e, cudaStreamSynchronize(d.stream));

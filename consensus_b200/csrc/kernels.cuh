@@ -126,8 +126,7 @@ __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restr
     }
     if (cnt == 0) return;
     uint32_t inv[N];
-    extern __shared__ uint32_t ninv_tab[];  // 16 * N words per thread, bank = lane
-    n_inv<C>(inv, run, ninv_tab, blockDim.x, threadIdx.x);
+    n_inv<C>(inv, run);
     for (int k = cnt - 1; k >= 0; k--) {
         uint32_t idx = t + (uint32_t)k * T;
         uint32_t w[N], m[N];
@@ -183,20 +182,13 @@ __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restr
     }
 }
 
-// host-side launcher of k_prep (dynamic shared memory = the inversion window table of each thread)
+// host-side launcher of k_prep
 template <class C, int W, int S>
 inline cudaError_t launch_prep(uint32_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_dig, uint32_t dlen, uint16_t *gidx,
                                int8_t *digits, uint8_t *flags, cudaStream_t st) {
     constexpr int PB = 128;
-    const size_t smem = (size_t)16 * C::N * 4 * PB;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t rc = cudaFuncSetAttribute(k_prep<C, W, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (rc != cudaSuccess) return rc;
-        attr_done = true;
-    }
     const uint32_t pthreads = (n + S - 1) / S;
-    k_prep<C, W, S><<<(pthreads + PB - 1) / PB, PB, smem, st>>>(n, d_r, d_s, d_dig, dlen, gidx, digits, flags);
+    k_prep<C, W, S><<<(pthreads + PB - 1) / PB, PB, 0, st>>>(n, d_r, d_s, d_dig, dlen, gidx, digits, flags);
     return cudaGetLastError();
 }
 

@@ -72,7 +72,13 @@ def test_field_ops(eng, curve):
     xs = [v for v in _edge_values(c.p, rng, 20) if v]
     got = _run(eng, curve, 4, [(x * R % c.p, 0) for x in xs], [(0, 0)] * len(xs))
     assert [g[0] for g in got] == [pow(x, -1, c.p) * R % c.p for x in xs]
-    xs = [v for v in _edge_values(c.n, rng, 20) if v]
+    # scalar-field inverse (binary extended GCD): many random values plus powers of two and their
+    # neighbours, which exercise long runs of trailing zeros (tz = 31 passes, zero low words)
+    xs = [v for v in _edge_values(c.n, rng, 1500) if v]
+    xs += [pow(2, k, c.n) for k in (1, 31, 32, 33, 63, 64, 65, 96, 128, 255, 256, 300, 383)]
+    xs += [(pow(2, k, c.n) * pow(R, -1, c.n)) % c.n for k in (32, 64, 96, 200)]   # residue itself a power of two
+    xs += [(c.n - pow(2, k, c.n)) % c.n for k in (1, 32, 64, 128)]
+    xs = [v for v in xs if v]
     got = _run(eng, curve, 8, [(x * R % c.n, 0) for x in xs], [(0, 0)] * len(xs))
     assert [g[0] for g in got] == [pow(x, -1, c.n) * R % c.n for x in xs]
 
