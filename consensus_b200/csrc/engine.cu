@@ -131,6 +131,7 @@ int launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t 
                   cudaStream_t st) {
     if (n == 0) return 0;
     if (curve == SBV_P256) {
+        if (e->p256_variant == 2) return sbv_launch_p256_coz_b448(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
         if (e->p256_variant == 1) return sbv_launch_p256_coz_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
         return sbv_launch_p256_w3_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
     }
@@ -434,6 +435,32 @@ int sbv_verify_batch_device(sbv_engine *e, int device_index, uint8_t curve, size
     return launch_verify(e, d, curve, n, d_r, d_s, d_qx, d_qy, d_digest, digest_len, d_ok, st);
 }
 
+// Enqueues H2D, both kernels and the verdict D2H of items [lo, lo + cnt) of a single-device call on
+// lane `lane` (no synchronisation).
+static int enqueue_range_1dev(sbv_engine *e, int lane, uint8_t curve, size_t lo, size_t cnt, const uint8_t *r, const uint8_t *s,
+                              const uint8_t *qx, const uint8_t *qy, const uint8_t *digest, uint8_t digest_len, uint8_t *ok) {
+    const size_t L = fbytes(curve);
+    Dev &d = e->devs[0];
+    Dev::Lane &ln = d.lanes[lane];
+    CU(e, cudaSetDevice(d.ordinal));
+    int rc = sbv_lane_ensure(e, d, ln, cnt, cnt * (4 * L + digest_len + 1) + 8 * 256);
+    if (rc) return rc;
+    size_t so = 0;
+    if ((rc = sbv_lane_h2d(e, ln, ln.d_r, r + lo * L, cnt * L, so))) return rc;
+    if ((rc = sbv_lane_h2d(e, ln, ln.d_s, s + lo * L, cnt * L, so))) return rc;
+    if ((rc = sbv_lane_h2d(e, ln, ln.d_dig, digest + lo * digest_len, cnt * digest_len, so))) return rc;
+    if ((rc = sbv_lane_h2d(e, ln, ln.d_qx, qx + lo * L, cnt * L, so))) return rc;
+    if ((rc = sbv_lane_h2d(e, ln, ln.d_qy, qy + lo * L, cnt * L, so))) return rc;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        rc = ensure_workspace(e, d, cnt);
+        if (!rc) rc = launch_verify(e, d, curve, cnt, ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, digest_len, ln.d_ok, ln.stream);
+    }
+    if (rc) return rc;
+    CU(e, cudaMemcpyAsync(ok + lo, ln.d_ok, cnt, cudaMemcpyDeviceToHost, ln.stream));
+    return 0;
+}
+
 int sbv_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *r, const uint8_t *s, const uint8_t *qx,
                      const uint8_t *qy, const uint8_t *digest, uint8_t digest_len, uint8_t *ok) {
     if (!e || curve > SBV_P384 || digest_len == 0 || (digest_len & 3) || digest_len > 64)
@@ -446,7 +473,15 @@ int sbv_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *r, c
     // A call owns one lane (stream + buffers) on every device; the engine lock is held only while
     // kernels are enqueued, so a second host thread overlaps its copies and kernels with ours.
     const int lane = sbv_lane_acquire(e);
-    struct Release { sbv_engine *e; int lane; ~Release() { sbv_lane_release(e, lane); } } release{e, lane};
+    struct Release { sbv_engine *e; int lane; ~Release() { if (lane >= 0) sbv_lane_release(e, lane); } } release{e, lane};
+    if (G == 1) {
+        // (Splitting one call over both lanes was measured: no gain for one caller — the two half-size
+        // verify kernels share the SMs like one launch — and it serialises two concurrent callers.)
+        int rc = enqueue_range_1dev(e, lane, curve, 0, n, r, s, qx, qy, digest, digest_len, ok);
+        if (rc) return rc;
+        CU(e, cudaStreamSynchronize(e->devs[0].lanes[lane].stream));
+        return SBV_OK;
+    }
     for (int g = 0; g < G; g++) {
         Dev &d = e->devs[g];
         Dev::Lane &ln = d.lanes[lane];
@@ -467,9 +502,8 @@ int sbv_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *r, c
             if (!rc) rc = launch_verify(e, d, curve, sh.n, ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, digest_len, ln.d_ok, ln.stream);
         }
         if (rc) return rc;
-        if (G == 1) CU(e, cudaMemcpyAsync(ok + sh.lo, ln.d_ok, sh.n, cudaMemcpyDeviceToHost, ln.stream));
     }
-    if (G > 1) {
+    {
         std::lock_guard<std::mutex> lk(e->mu);  // the gather buffers are per device, not per lane
         int rc = gather_verdicts(e, n, lane);
         if (rc) return rc;
@@ -478,10 +512,7 @@ int sbv_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *r, c
             CU(e, cudaStreamSynchronize(e->devs[g].lanes[lane].stream));
         }
         unpack_verdicts(e, n, ok);
-        return SBV_OK;
     }
-    CU(e, cudaSetDevice(e->devs[0].ordinal));
-    CU(e, cudaStreamSynchronize(e->devs[0].lanes[lane].stream));
     return SBV_OK;
 }
 

@@ -450,7 +450,9 @@ __global__ void __launch_bounds__(BLOCK) k_verify_keyed(uint32_t n, const uint32
 // live in shared memory (448 B per thread, bank = lane), 1Q and Zc, Zc^2, Zc^3 in a coalesced global
 // scratch (tscr[40][n]).  65 additions of 11M+3S instead of the 86 of 12M+4S a 3-bit Jacobian table
 // needs at the same single-wave occupancy (7 blocks of 64 threads per SM).
-template <class C, int BLOCK, int MINB>
+// LOCKSTEP: one big block per SM with a block barrier per window, so the warps of an SM progress
+// together and finish together (a single-wave launch otherwise ends with stragglers issuing alone).
+template <class C, int BLOCK, int MINB, bool LOCKSTEP = false>
 __global__ void __launch_bounds__(BLOCK, MINB) k_verify_coz(uint32_t n, const uint8_t *__restrict__ qx_be, const uint8_t *__restrict__ qy_be,
                                                              const uint8_t *__restrict__ r_be, const uint16_t *__restrict__ gidx,
                                                              const int8_t *__restrict__ digits, const uint8_t *__restrict__ flags,
@@ -461,8 +463,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_verify_coz(uint32_t n, const ui
     constexpr int NWIN = Windows<32 * N, W>::COUNT;
     extern __shared__ uint32_t tab[];  // entries 2..8: [((k-2)*2 + coord)*N + limb][BLOCK]
     const uint32_t tid = threadIdx.x;
-    const uint32_t idx = blockIdx.x * BLOCK + tid;
-    if (idx >= n) return;
+    uint32_t idx = blockIdx.x * BLOCK + tid;
+    const bool live = idx < n;
+    if (!LOCKSTEP && !live) return;
+    if (!live) idx = n - 1;  // LOCKSTEP: surplus threads shadow the last item so every barrier is reached
 #define TAB(k, c, w) tab[((((k) - 2) * 2 + (c)) * N + (w)) * BLOCK + tid]
 #define SCR(w) tscr[(size_t)(w) * n + idx]
     // scratch words: [0,2N) entry 1 (x, y) ; [2N,3N) Zc ; [3N,4N) Zc^2 ; [4N,5N) Zc^3 ; [5N, 12N) H_2..H_8
@@ -563,6 +567,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_verify_coz(uint32_t n, const ui
             zc[i] = SCR(2 * N + i); zc2[i] = SCR(3 * N + i); zc3[i] = SCR(4 * N + i);
         }
         pt_add_m<C, 2>(acc, x2, y2, zc, zc2, zc3, neg, skip);
+        if (LOCKSTEP) __syncthreads();
     }
     {
         constexpr int EU4 = 2 * N / 4;
@@ -579,6 +584,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_verify_coz(uint32_t n, const ui
             }
             pt_add<C, true>(acc, gx, gy, one, false, gb == 0);
             if (win + 1 < C::GWINS) { mp_copy<N>(gx, ngx); mp_copy<N>(gy, ngy); gb = ngb; }
+            if (LOCKSTEP) __syncthreads();
         }
     }
 #undef TAB
@@ -602,7 +608,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_verify_coz(uint32_t n, const ui
             match = mp_eq<N>(lhs, acc.X);
         }
     }
-    ok_out[idx] = (good && match) ? 1 : 0;
+    if (live) ok_out[idx] = (good && match) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------

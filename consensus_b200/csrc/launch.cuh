@@ -44,7 +44,7 @@ int launch_verify_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const u
 }
 
 // co-Z 4-bit-window variant (k_verify_coz)
-template <class C, int BLOCK, int MINB>
+template <class C, int BLOCK, int MINB, bool LOCKSTEP = false>
 int launch_verify_coz_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                         const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st, int curve_idx) {
     constexpr int S = 8;
@@ -67,10 +67,10 @@ int launch_verify_coz_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, con
     const size_t smem = (size_t)7 * 2 * C::N * 4 * BLOCK;
     static bool attr_done = false;
     if (!attr_done) {
-        CU(e, cudaFuncSetAttribute(k_verify_coz<C, BLOCK, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(e, cudaFuncSetAttribute(k_verify_coz<C, BLOCK, MINB, LOCKSTEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    k_verify_coz<C, BLOCK, MINB><<<(nn + BLOCK - 1) / BLOCK, BLOCK, smem, st>>>(
+    k_verify_coz<C, BLOCK, MINB, LOCKSTEP><<<(nn + BLOCK - 1) / BLOCK, BLOCK, smem, st>>>(
         nn, d_qx, d_qy, d_r, w->gidx, w->digits, w->flags, reinterpret_cast<const uint4 *>(d.gtab[curve_idx]), w->tscr, d_ok);
     if (ev) CU(e, cudaEventRecord(ev[2], st));
     CU(e, cudaEventRecord(w->done, st));
@@ -80,6 +80,12 @@ int launch_verify_coz_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, con
 }
 
 }  // namespace sbv
+
+#define SBV_DEFINE_LAUNCHER_COZ_LOCKSTEP(NAME, CURVE, BLOCK, IDX)                                                            \
+    int NAME(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,               \
+             const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st) {                 \
+        return sbv::launch_verify_coz_t<sbv::CURVE, BLOCK, 1, true>(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st, IDX); \
+    }
 
 #define SBV_DEFINE_LAUNCHER_COZ(NAME, CURVE, BLOCK, MINB, IDX)                                                              \
     int NAME(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,               \

@@ -293,3 +293,27 @@ def test_concurrent_callers_share_the_engine(eng):
     for t in ths: t.start()
     for t in ths: t.join()
     assert not errs, errs
+
+
+def test_hash_verify_registered_fused(eng):
+    """SHA-256 on the device feeding the registered-key verify (the call GpuVerifier / the Go shim make)."""
+    n, K = 1500, 6
+    msgs, off = corpus.make_requests(n, seed=15, fixed_len=None, lo=1, hi=900)
+    dig = oracle.sha256_batch(msgs, off)
+    d, kxy = corpus.make_keys(P256, K, seed=111)
+    key_idx = (np.arange(n) % K).astype(np.uint32)
+    r, s = oracle.sign_batch(P256, d, key_idx, dig, corpus._blocks(113, n, 32, b"k"))
+    msgs = msgs.copy()
+    for i in range(0, n, 6):
+        msgs[int(off[i])] ^= 0x80            # tampered message
+    for i in range(3, n, 9):
+        r[i, 31] ^= 1                        # tampered signature
+    slot = key_idx.copy(); slot[5::50] = (slot[5::50] + 1) % K   # wrong signer
+    eng.set_keys(np.zeros(K, np.uint8), kxy.reshape(K, 2, 32))
+    keys_of = kxy[slot]
+    want = oracle.verify_batch(P256, r, s, np.ascontiguousarray(keys_of[:, :32]), np.ascontiguousarray(keys_of[:, 32:]),
+                               oracle.sha256_batch(msgs, off))
+    got = eng.hash_verify_registered(P256, msgs, off, slot, r, s)
+    assert (got == want).all()
+    assert 0 < want.sum() < n
+    assert (eng.hash_verify_registered(P256, msgs, off[:8], slot[:7], r[:7], s[:7]) == want[:7]).all()   # warp path
