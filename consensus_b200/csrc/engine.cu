@@ -54,7 +54,7 @@ int ensure_workspace(sbv_engine *e, Dev &d, size_t n) {
         CU(e, cudaMalloc(&w.gidx, cap * 48 * sizeof(uint16_t)));
         CU(e, cudaMalloc(&w.flags, cap));
         CU(e, cudaMalloc(&w.digits, cap * 132));
-        CU(e, cudaMalloc(&w.tscr, cap * 12 * 8 * sizeof(uint32_t)));
+        CU(e, cudaMalloc(&w.tscr, cap * 12 * 12 * sizeof(uint32_t)));  // 12N words per signature, N = 12 for P-384
     }
     d.cap = cap;
     return 0;
@@ -135,6 +135,7 @@ int launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t 
         if (e->p256_variant == 1) return sbv_launch_p256_coz_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
         return sbv_launch_p256_w3_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
     }
+    if (e->p384_variant == 1) return sbv_launch_p384_coz_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
     return sbv_launch_p384_w3_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
 }
 
@@ -352,6 +353,7 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
     if (cudaGetDeviceCount(&count) != cudaSuccess || count < n_devices) return SBV_ERR_CUDA;
     sbv_engine *e = new sbv_engine();
     e->p256_variant = env_int("SBV_P256_VARIANT", 1);
+    e->p384_variant = env_int("SBV_P384_VARIANT", 1);
     e->keyed_warp_limit = env_int("SBV_KEYED_WARP_LIMIT", 2048);
     e->devs.resize(n_devices);
     for (int g = 0; g < n_devices; g++) {

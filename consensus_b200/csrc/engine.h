@@ -71,6 +71,7 @@ struct sbv_engine {
     std::string err;
     uint64_t launches = 0;
     int keyed_warp_limit = 2048;  // registered-key batches up to this size use one warp per signature (SBV_KEYED_WARP_LIMIT)
+    int p384_variant = 1;  // 1 = co-Z 4-bit window, 0 = 3-bit Jacobian window (SBV_P384_VARIANT)
     int p256_variant = 1;  // 1 = co-Z 4-bit window (default), 2 = co-Z with one lockstep 448-thread block per SM, 0 = 3-bit Jacobian window
     bool profiling = false;
     // NCCL (multi-device only; loaded lazily with dlopen so single-device users never touch it)
@@ -110,6 +111,8 @@ int sbv_launch_p256_coz_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r,
                             const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
 int sbv_launch_p256_coz_b448(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                              const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
+int sbv_launch_p384_coz_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
+                            const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
 int sbv_launch_p384_w3_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                             const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
 int sbv_init_gtables(sbv_engine *e, Dev &d);  // gtable.cu
