@@ -366,8 +366,8 @@ __global__ void k_keytab_init(uint32_t n_keys, const uint8_t *__restrict__ keys_
     for (int i = 0; i < N; i++) { out[i] = ox[i]; out[N + i] = oy[i]; }
 }
 
-template <class C, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_verify_keyed(uint32_t n, const uint32_t *__restrict__ slot, const int32_t *__restrict__ slot2local,
+template <class C, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_verify_keyed(uint32_t n, const uint32_t *__restrict__ slot, const int32_t *__restrict__ slot2local,
                                                         uint32_t n_slots, const uint8_t *__restrict__ keyflags,
                                                         const uint8_t *__restrict__ r_be, const uint16_t *__restrict__ gidx,
                                                         const uint8_t *__restrict__ qidx, const uint8_t *__restrict__ flags,

@@ -61,10 +61,10 @@ int sbv_keys_build(sbv_engine *e, Dev &d) {
     return 0;
 }
 
-template <class C>
+template <class C, int BLOCK, int MINB>
 static int launch_keyed_t(sbv_engine *e, Dev &d, int c, size_t n, const uint32_t *d_slot, const uint8_t *d_r, const uint8_t *d_s,
                           const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st) {
-    constexpr int S = 8, BLOCK = 128;
+    constexpr int S = 8;
     const uint32_t nn = (uint32_t)n;
     Dev::Scratch *w = nullptr;
     if (int rc = sbv_take_scratch(e, d, st, &w)) return rc;
@@ -87,7 +87,7 @@ static int launch_keyed_t(sbv_engine *e, Dev &d, int c, size_t n, const uint32_t
             nn, d_slot, d.slot2local[c], d.n_slots, d.keyflags[c], d_r, w->gidx, reinterpret_cast<const uint8_t *>(w->digits), w->flags,
             reinterpret_cast<const uint4 *>(d.gtab[c]), reinterpret_cast<const uint4 *>(d.ktab[c]), d_ok);
     else
-    k_verify_keyed<C, BLOCK><<<(nn + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(
+    k_verify_keyed<C, BLOCK, MINB><<<(nn + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(
         nn, d_slot, d.slot2local[c], d.n_slots, d.keyflags[c], d_r, w->gidx, reinterpret_cast<const uint8_t *>(w->digits), w->flags,
         reinterpret_cast<const uint4 *>(d.gtab[c]), reinterpret_cast<const uint4 *>(d.ktab[c]), d_ok);
     if (ev) CU(e, cudaEventRecord(ev[2], st));
@@ -104,8 +104,9 @@ int sbv_launch_keyed(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint3
         CU(e, cudaMemsetAsync(d_ok, 0, n, st));
         return 0;
     }
-    if (curve == SBV_P256) return launch_keyed_t<P256>(e, d, 0, n, d_slot, d_r, d_s, d_dig, dlen, d_ok, st);
-    return launch_keyed_t<P384>(e, d, 1, n, d_slot, d_r, d_s, d_dig, dlen, d_ok, st);
+    // P-256: 7 blocks of 64 threads per SM = 66,304 resident threads >= one 65,536 batch (single wave)
+    if (curve == SBV_P256) return launch_keyed_t<P256, 64, 7>(e, d, 0, n, d_slot, d_r, d_s, d_dig, dlen, d_ok, st);
+    return launch_keyed_t<P384, 64, 4>(e, d, 1, n, d_slot, d_r, d_s, d_dig, dlen, d_ok, st);
 }
 
 extern "C" {
