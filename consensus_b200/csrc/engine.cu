@@ -99,6 +99,9 @@ int ensure_msgs(sbv_engine *e, Dev &d, size_t bytes, size_t n_off) {
         d.d_off = nullptr;
         size_t cap = n_off + n_off / 8 + 1024;
         CU(e, cudaMalloc(&d.d_off, cap * sizeof(uint64_t)));
+        if (d.d_perm) cudaFree(d.d_perm);
+        d.d_perm = nullptr;
+        CU(e, cudaMalloc(&d.d_perm, (cap + 3 * 1024) * sizeof(uint32_t)));
         d.off_cap = cap;
     }
     return 0;
@@ -214,12 +217,26 @@ int sbv_lane_ensure_msgs(sbv_engine *e, Dev::Lane &ln, size_t bytes, size_t n_of
         ln.d_off = nullptr;
         const size_t cap = n_off + n_off / 8 + 1024;
         CU(e, cudaMalloc(&ln.d_off, cap * sizeof(uint64_t)));
+        if (ln.d_perm) cudaFree(ln.d_perm);
+        ln.d_perm = nullptr;
+        CU(e, cudaMalloc(&ln.d_perm, (cap + 3 * 1024) * sizeof(uint32_t)));
         ln.off_cap = cap;
     }
     return 0;
 }
-int sbv_launch_sha256(sbv_engine *e, size_t n, const uint8_t *d_msgs, const uint64_t *d_off, uint64_t base, uint8_t *d_digest, cudaStream_t st) {
-    k_sha256<<<(uint32_t)((n + 127) / 128), 128, 0, st>>>((uint32_t)n, d_msgs, d_off, base, d_digest);
+int sbv_launch_sha256(sbv_engine *e, size_t n, const uint8_t *d_msgs, const uint64_t *d_off, uint64_t base, uint8_t *d_digest, uint32_t *d_perm,
+                      cudaStream_t st) {
+    const uint32_t *perm = nullptr;
+    if (d_perm && n >= 2048) {  // sort by block count so that a warp's 32 messages have equal length
+        uint32_t *hist = d_perm + n, *start = hist + SHA_BINS, *cursor = start + SHA_BINS;
+        CU(e, cudaMemsetAsync(hist, 0, SHA_BINS * sizeof(uint32_t), st));
+        k_sha_hist<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>((uint32_t)n, d_off, hist);
+        k_sha_scan<<<1, SHA_BINS, 0, st>>>(hist, start, cursor);
+        k_sha_scatter<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>((uint32_t)n, d_off, start, cursor, d_perm);
+        e->launches += 3;
+        perm = d_perm;
+    }
+    k_sha256<<<(uint32_t)((n + 127) / 128), 128, 0, st>>>((uint32_t)n, d_msgs, d_off, base, d_digest, perm);
     e->launches += 1;
     CU(e, cudaGetLastError());
     return 0;
@@ -389,7 +406,7 @@ void sbv_destroy(sbv_engine *e) {
     for (Dev &d : e->devs) {
         cudaSetDevice(d.ordinal);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        void *ptrs[] = {d.gtab[0], d.gtab[1], d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, d.d_ok,  d.d_msgs, d.d_off, d.d_scratch};
+        void *ptrs[] = {d.gtab[0], d.gtab[1], d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, d.d_ok,  d.d_msgs, d.d_off, d.d_perm, d.d_scratch};
         for (auto &w : d.ws) {
             void *wp[] = {w.gidx, w.flags, w.digits, w.tscr};
             for (void *p : wp) if (p) cudaFree(p);
@@ -399,7 +416,7 @@ void sbv_destroy(sbv_engine *e) {
         sbv_keys_free(d);
         for (auto &ln : d.lanes) {
             if (ln.stream) cudaStreamSynchronize(ln.stream);
-            void *lp[] = {ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, ln.d_ok, ln.d_slot, ln.d_msgs, ln.d_off};
+            void *lp[] = {ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, ln.d_ok, ln.d_slot, ln.d_msgs, ln.d_off, ln.d_perm};
             for (void *p : lp) if (p) cudaFree(p);
             if (ln.h_pin) cudaFreeHost(ln.h_pin);
             if (ln.stream) cudaStreamDestroy(ln.stream);

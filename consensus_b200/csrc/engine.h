@@ -39,6 +39,7 @@ struct Dev {
         uint32_t *d_slot = nullptr;
         uint8_t *d_msgs = nullptr;
         uint64_t *d_off = nullptr;
+        uint32_t *d_perm = nullptr;  // off_cap entries + 3 * 1024 words of sort state
         size_t msg_cap = 0, off_cap = 0;
         uint8_t *h_pin = nullptr;
         size_t h_pin_cap = 0;
@@ -47,6 +48,7 @@ struct Dev {
     size_t msg_cap = 0, off_cap = 0;
     uint8_t *d_msgs = nullptr;
     uint64_t *d_off = nullptr;
+    uint32_t *d_perm = nullptr;
     // pinned staging
     uint8_t *h_pin = nullptr;
     size_t h_pin_cap = 0;
@@ -127,7 +129,9 @@ int sbv_lane_acquire(sbv_engine *e);            // blocks until a lane index is 
 void sbv_lane_release(sbv_engine *e, int lane);
 int sbv_lane_ensure(sbv_engine *e, Dev &d, Dev::Lane &ln, size_t n, size_t pinned_bytes);
 int sbv_lane_ensure_msgs(sbv_engine *e, Dev::Lane &ln, size_t bytes, size_t n_off);
-int sbv_launch_sha256(sbv_engine *e, size_t n, const uint8_t *d_msgs, const uint64_t *d_off, uint64_t base, uint8_t *d_digest, cudaStream_t st);
+// d_perm: n + 3072 words of scratch (may be null: no length sort)
+int sbv_launch_sha256(sbv_engine *e, size_t n, const uint8_t *d_msgs, const uint64_t *d_off, uint64_t base, uint8_t *d_digest, uint32_t *d_perm,
+                      cudaStream_t st);
 int sbv_lane_h2d(sbv_engine *e, Dev::Lane &ln, void *dst, const void *src, size_t bytes, size_t &stage_off);
 int sbv_ensure_scratch(sbv_engine *e, Dev &d, size_t bytes);
 // takes the next scratch set of device d for a launch on stream st (waits for its previous user)

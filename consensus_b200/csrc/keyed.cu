@@ -195,7 +195,7 @@ int sbv_hash_verify_registered(sbv_engine *e, uint8_t curve, size_t n, const uin
         if ((rc = sbv_lane_h2d(e, ln, ln.d_s, s + lo * L, cnt * L, so))) return rc;
         {
             std::lock_guard<std::mutex> lk(e->mu);
-            rc = sbv_launch_sha256(e, cnt, ln.d_msgs, ln.d_off, msg_off[lo], ln.d_dig, ln.stream);
+            rc = sbv_launch_sha256(e, cnt, ln.d_msgs, ln.d_off, msg_off[lo], ln.d_dig, ln.d_perm, ln.stream);
             if (!rc) rc = sbv_ensure_workspace(e, d, cnt);
             if (!rc) rc = sbv_launch_keyed(e, d, curve, cnt, ln.d_slot, ln.d_r, ln.d_s, ln.d_dig, 32, ln.d_ok, ln.stream);
         }

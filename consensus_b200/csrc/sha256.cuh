@@ -43,10 +43,15 @@ __device__ __forceinline__ void sha256_compress(uint32_t (&h)[8], uint32_t (&w)[
 }
 
 // digest_out: 32 bytes per message, big-endian words (the byte string SHA-256 defines)
+// perm (optional): message processed by thread t is perm[t] — the launcher sorts messages by block
+// count (longest first) so the 32 lanes of a warp hash messages of equal length instead of all
+// waiting for the longest one.
 __global__ void __launch_bounds__(128) k_sha256(uint32_t n, const uint8_t *__restrict__ msgs,
-                                                const uint64_t *__restrict__ off, uint64_t base, uint8_t *__restrict__ digest_out) {
-    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
+                                                const uint64_t *__restrict__ off, uint64_t base, uint8_t *__restrict__ digest_out,
+                                                const uint32_t *__restrict__ perm) {
+    const uint32_t tix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tix >= n) return;
+    const uint32_t idx = perm ? perm[tix] : tix;
     const uint64_t o = off[idx] - base;
     const uint64_t len = off[idx + 1] - off[idx];
     const uint32_t *words = reinterpret_cast<const uint32_t *>(msgs + (o & ~(uint64_t)3));
@@ -56,8 +61,8 @@ __global__ void __launch_bounds__(128) k_sha256(uint32_t n, const uint8_t *__res
     const uint64_t nblocks = (len + 9 + 63) / 64;
     for (uint64_t blk = 0; blk < nblocks; blk++) {
         uint32_t w[16];
-        const uint64_t base = blk * 64;
-        if (base + 64 <= len) {
+        const uint64_t bpos = blk * 64;
+        if (bpos + 64 <= len) {
             uint32_t prev = __ldg(words + blk * 16);
 #pragma unroll
             for (int j = 0; j < 16; j++) {
@@ -68,7 +73,7 @@ __global__ void __launch_bounds__(128) k_sha256(uint32_t n, const uint8_t *__res
         } else {
 #pragma unroll
             for (int j = 0; j < 16; j++) {
-                const uint64_t p = base + 4 * (uint64_t)j;
+                const uint64_t p = bpos + 4 * (uint64_t)j;
                 uint32_t v = 0;
                 if (p < len) {
                     uint32_t a = __ldg(words + blk * 16 + j), b = __ldg(words + blk * 16 + j + 1);
@@ -91,6 +96,53 @@ __global__ void __launch_bounds__(128) k_sha256(uint32_t n, const uint8_t *__res
     uint4 *out = reinterpret_cast<uint4 *>(digest_out + (size_t)idx * 32);
     out[0] = make_uint4(__byte_perm(h[0], 0, 0x0123), __byte_perm(h[1], 0, 0x0123), __byte_perm(h[2], 0, 0x0123), __byte_perm(h[3], 0, 0x0123));
     out[1] = make_uint4(__byte_perm(h[4], 0, 0x0123), __byte_perm(h[5], 0, 0x0123), __byte_perm(h[6], 0, 0x0123), __byte_perm(h[7], 0, 0x0123));
+}
+
+// ---- counting sort of the messages by SHA-256 block count (descending) ----
+constexpr int SHA_BINS = 1024;  // bin = min(nblocks, 1023): exact up to 65 KB messages
+__device__ __forceinline__ uint32_t sha_bin(const uint64_t *off, uint32_t i) {
+    const uint64_t nb = (off[i + 1] - off[i] + 9 + 63) / 64;
+    return nb < SHA_BINS ? (uint32_t)nb : SHA_BINS - 1;
+}
+__global__ void k_sha_hist(uint32_t n, const uint64_t *__restrict__ off, uint32_t *__restrict__ hist) {
+    __shared__ uint32_t h[SHA_BINS];
+    for (int i = threadIdx.x; i < SHA_BINS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&h[sha_bin(off, i)], 1u);
+    __syncthreads();
+    for (int b = threadIdx.x; b < SHA_BINS; b += blockDim.x) if (h[b]) atomicAdd(&hist[b], h[b]);
+}
+// one block of SHA_BINS threads: start[b] = number of messages in bins > b (longest first); cursor = 0
+__global__ void k_sha_scan(const uint32_t *__restrict__ hist, uint32_t *__restrict__ start, uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t s[SHA_BINS];
+    const int b = threadIdx.x;
+    s[b] = hist[SHA_BINS - 1 - b];  // reversed: position b holds bin SHA_BINS-1-b
+    __syncthreads();
+    for (int d = 1; d < SHA_BINS; d <<= 1) {
+        uint32_t v = b >= d ? s[b - d] : 0u;
+        __syncthreads();
+        s[b] += v;
+        __syncthreads();
+    }
+    start[SHA_BINS - 1 - b] = s[b] - hist[SHA_BINS - 1 - b];  // exclusive
+    cursor[b] = 0;
+}
+__global__ void k_sha_scatter(uint32_t n, const uint64_t *__restrict__ off, const uint32_t *__restrict__ start,
+                              uint32_t *__restrict__ cursor, uint32_t *__restrict__ perm) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const uint32_t b = valid ? sha_bin(off, i) : 0xffffffffu;
+    // warp-aggregated: one atomic per distinct bin per warp (a batch of equal-length messages would
+    // otherwise serialise a million atomics on one counter); ranks keep the input order inside a warp
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t peers = __match_any_sync(0xffffffffu, b);
+    const int leader = __ffs((int)peers) - 1;
+    const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    uint32_t base = 0;
+    if (valid && (int)lane == leader) base = atomicAdd(&cursor[b], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    if (valid) perm[start[b] + base + rank] = i;
 }
 
 }  // namespace sbv
