@@ -29,8 +29,10 @@
  *  - Accept set = Go crypto/ecdsa (Verify / VerifyASN1): key must be an on-curve affine point with
  *    coordinates < p; r, s in [1, n-1]; e = leftmost min(len, 32|48) digest bytes; R = (e/s)G +
  *    (r/s)Q must not be infinity; accept iff R.x mod n == r.  No low-S rule.
- *  - Thread-safe: calls on one engine serialise on an internal lock; the CUDA device is set
- *    explicitly per call, so calls may come from any OS thread (cgo).
+ *  - Thread-safe and re-entrant: the CUDA device is set explicitly per call, so calls may come from any
+ *    OS thread (cgo).  sbv_verify_batch / sbv_verify_registered / sbv_hash_verify_registered each own a
+ *    lane (stream, buffers, pinned staging) for the duration of the call — two calls proceed concurrently
+ *    and overlap their copies and kernels; a third waits.  The other entry points serialise on the engine lock.
  *  - There is no CPU fallback: without a usable CUDA device sbv_create fails.
  */
 #ifndef SBV_H
