@@ -47,8 +47,9 @@ int launch_verify_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const u
 template <class C, int BLOCK, int MINB, bool LOCKSTEP = false>
 int launch_verify_coz_t(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                         const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st, int curve_idx) {
-    constexpr int S = 8;
+    
     const uint32_t nn = (uint32_t)n;
+    constexpr int S = 8;
     Dev::Scratch *w = nullptr;
     if (int rc = sbv_take_scratch(e, d, st, &w)) return rc;
     cudaEvent_t *ev = nullptr;
