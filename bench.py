@@ -199,28 +199,48 @@ def main():
     lanes = [torch.cuda.Stream(device=dev) for _ in range(N_LANES)]
     d_oks = [torch.zeros(BATCH, dtype=torch.uint8, device=dev) for _ in range(N_LANES)]
 
+    # The verdict gather (pack to a bitmask + NCCL all_gather) of every step runs on ONE dedicated stream,
+    # chained by events: collectives of one communicator execute in issue order, so issuing them on the
+    # lane streams would re-serialise the lanes at every gather.
+    gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    verify_done = [torch.cuda.Event() for _ in range(N_LANES)]
+    gather_done = [None] * N_LANES
+
     def device_step(i, pipelined=True):
         c = copies[i % N_COPIES]
         if not pipelined:
             eng.verify_batch_device(sbv.P256, BATCH, c["r"].data_ptr(), c["s"].data_ptr(), c["qx"].data_ptr(), c["qy"].data_ptr(),
                                     c["digest"].data_ptr(), 32, d_ok.data_ptr(), stream=stream)
             return
-        lane = lanes[i % N_LANES]
-        out = d_oks[i % N_LANES]
+        k = i % N_LANES
+        lane, out = lanes[k], d_oks[k]
         with torch.cuda.stream(lane):
+            if gather_done[k] is not None:
+                lane.wait_event(gather_done[k])      # the previous user's verdicts have been packed
             eng.verify_batch_device(sbv.P256, BATCH, c["r"].data_ptr(), c["s"].data_ptr(), c["qx"].data_ptr(), c["qy"].data_ptr(),
                                     c["digest"].data_ptr(), 32, out.data_ptr(), stream=lane.cuda_stream)
             if world > 1:
+                verify_done[k].record(lane)
+        if world > 1:
+            with torch.cuda.stream(gather_stream):
+                gather_stream.wait_event(verify_done[k])
                 packed = (out.view(-1, 8) * pow2).sum(dim=1, dtype=torch.uint8)  # 8 KiB verdict bitmask
+                ev = torch.cuda.Event()
+                ev.record(gather_stream)
+                gather_done[k] = ev                  # `out` may be overwritten once it has been packed
                 dist.all_gather_into_tensor(gathered, packed)
 
     def join_lanes():
         for lane in lanes:
             torch.cuda.current_stream().wait_stream(lane)
+        if gather_stream is not None:
+            torch.cuda.current_stream().wait_stream(gather_stream)
 
     def fork_lanes():
         for lane in lanes:
             lane.wait_stream(torch.cuda.current_stream())
+        if gather_stream is not None:
+            gather_stream.wait_stream(torch.cuda.current_stream())
 
     def barrier():
         if world > 1:
@@ -397,7 +417,7 @@ def main():
         "config": {"workload": "C2: ECDSA-P256 batch verify, 65,536 synthetic sigs per GPU, 1,024 keys, 1/16 corrupted",
                    "batch_per_gpu": BATCH, "l2": f"{N_COPIES} rotating input copies (168 MB > 126 MB L2)",
                    "pipelining": "consecutive steps rotate over 3 CUDA streams; unpipelined step latency in step_latency_ms",
-                   "exchange": "NCCL all_gather of the packed verdict bitmask per step" if world > 1 else "none (1 GPU)",
+                   "exchange": "NCCL all_gather of the packed verdict bitmask per step, on a dedicated stream chained by events" if world > 1 else "none (1 GPU)",
                    "sharding": f"batch-parallel x{world}"},
         "e2e": {"value": e2e_value, "unit": "verifies/s", "h2d_bytes_per_step": 160 * BATCH * world, "d2h_bytes_per_step": BATCH * world,
                 "callers": 2, "single_caller_value": e2e_single},
