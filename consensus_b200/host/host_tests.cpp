@@ -304,6 +304,10 @@ static void TestGpuVerifierEndToEnd() {
     Pool pool;
     for (int i = 0; i < 100; i++) { Bytes rq = reqs[i]; if (i % 10 == 0) rq[rq.size() - 1] ^= 1; pool.Submit(rq, {"alice", std::to_string(i)}); }
     CHECK(pool.Prune(v) == 10 && pool.Size() == 90);
+    // Proposal.Digest in batch on the GPU equals the host digest (types.go:50-69), incl. long-form DER lengths
+    std::vector<Proposal> props = {fixtureProposal(), fixtureWrongProposal(), Proposal{}, Proposal{Bytes(70000, 0x5a), {1, 2, 3}, Bytes(200, 7), -5}, prop, last};
+    auto dg = v.DigestBatch(props);
+    for (size_t i = 0; i < props.size(); i++) CHECK(dg[i] == props[i].Digest());
     for (auto &kv : keys) EC_KEY_free(kv.second.k);
     EC_KEY_free(ck.k);
 }

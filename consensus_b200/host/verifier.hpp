@@ -252,6 +252,26 @@ class GpuVerifier : public IVerifier {
         return ok;
     }
 
+    // Proposal.Digest for MANY proposals (pkg/types/types.go:50-69): DER framing on the host, every SHA-256
+    // chain on the GPU in one sbv_sha256_batch call.  (One digest is a single sequential chain and stays
+    // on the host: Proposal::Digest.)  Returns the hex strings the reference compares in verifyVote.
+    std::vector<std::string> DigestBatch(const std::vector<Proposal> &props) {
+        std::vector<std::string> out(props.size());
+        if (props.empty()) return out;
+        Bytes blob;
+        std::vector<uint64_t> off(props.size() + 1, 0);
+        for (size_t i = 0; i < props.size(); i++) {
+            Bytes d = props[i].Der();
+            blob.insert(blob.end(), d.begin(), d.end());
+            off[i + 1] = blob.size();
+        }
+        Bytes dig(props.size() * 32);
+        if (sbv_sha256_batch(eng_, props.size(), blob.data(), off.data(), dig.data()) != SBV_OK)
+            throw EngineFault(std::string("sbv_sha256_batch: ") + sbv_last_error(eng_));
+        for (size_t i = 0; i < props.size(); i++) out[i] = hex(Bytes(dig.begin() + 32 * i, dig.begin() + 32 * i + 32));
+        return out;
+    }
+
     // ---- api.Verifier ----
     std::pair<Bytes, Error> VerifyConsenterSig(const Signature &sig, const Proposal &prop) override {
         SigItem it;
