@@ -17,6 +17,7 @@ namespace sbv {
 struct Fe8 { uint32_t v[8]; };
 static __device__ __noinline__ Fe8 p256_fmul_call(Fe8 a, Fe8 b);
 static __device__ __noinline__ Fe8 p256_fsqr_call(Fe8 a);
+static __device__ __noinline__ Fe8 p256_nmul_call(Fe8 a, Fe8 b);
 
 struct P256 {
     static constexpr int N = 8;
@@ -128,15 +129,18 @@ struct P256 {
         const uint32_t p[8] = SBV_P256_P;
         mod_sub<8>(r, a, b, p);
     }
-    SBV_DEV static void nmul(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+    SBV_DEV static void nmul_inline(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
         const uint32_t n[8] = SBV_P256_N;
         const uint32_t ni[8] = SBV_P256_NINV_FULL;
         mont_mul_sos<8>(r, a, b, n, ni);
     }
-    SBV_DEV static void nsqr(uint32_t (&r)[8], const uint32_t (&a)[8]) {
-        const uint32_t n[8] = SBV_P256_N;
-        const uint32_t ni[8] = SBV_P256_NINV_FULL;
-        mont_sqr_sos<8>(r, a, n, ni);
+    // out of line: k_prep is latency-bound, and with its scalar multiplications inlined it overflowed
+    // the instruction cache (ncu: no_instruction was its top stall)
+    SBV_DEV static void nmul(uint32_t (&r)[8], const uint32_t (&a)[8], const uint32_t (&b)[8]) {
+        Fe8 x, y;
+        mp_copy<8>(x.v, a); mp_copy<8>(y.v, b);
+        Fe8 z = p256_nmul_call(x, y);
+        mp_copy<8>(r, z.v);
     }
 };
 
@@ -150,6 +154,11 @@ static __device__ __noinline__ Fe8 p256_fsqr_call(Fe8 a) {
     P256::fsqr_inline(r.v, a.v);
     return r;
 }
+static __device__ __noinline__ Fe8 p256_nmul_call(Fe8 a, Fe8 b) {
+    Fe8 r;
+    P256::nmul_inline(r.v, a.v, b.v);
+    return r;
+}
 
 // -------------------------------------------------------------------------------------------------
 // P-384: generic word-serial Montgomery for both fields (12 limbs).
@@ -157,6 +166,7 @@ static __device__ __noinline__ Fe8 p256_fsqr_call(Fe8 a) {
 struct Fe12 { uint32_t v[12]; };
 static __device__ __noinline__ Fe12 p384_fmul_call(Fe12 a, Fe12 b);
 static __device__ __noinline__ Fe12 p384_fsqr_call(Fe12 a);
+static __device__ __noinline__ Fe12 p384_nmul_call(Fe12 a, Fe12 b);
 
 struct P384 {
     static constexpr int N = 12;
@@ -265,15 +275,16 @@ struct P384 {
         const uint32_t p[12] = SBV_P384_P;
         mod_sub<12>(r, a, b, p);
     }
-    SBV_DEV static void nmul(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
+    SBV_DEV static void nmul_inline(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
         const uint32_t n[12] = SBV_P384_N;
         const uint32_t ni[12] = SBV_P384_NINV_FULL;
         mont_mul_sos<12>(r, a, b, n, ni);
     }
-    SBV_DEV static void nsqr(uint32_t (&r)[12], const uint32_t (&a)[12]) {
-        const uint32_t n[12] = SBV_P384_N;
-        const uint32_t ni[12] = SBV_P384_NINV_FULL;
-        mont_sqr_sos<12>(r, a, n, ni);
+    SBV_DEV static void nmul(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
+        Fe12 x, y;
+        mp_copy<12>(x.v, a); mp_copy<12>(y.v, b);
+        Fe12 z = p384_nmul_call(x, y);
+        mp_copy<12>(r, z.v);
     }
 };
 
@@ -285,6 +296,11 @@ static __device__ __noinline__ Fe12 p384_fmul_call(Fe12 a, Fe12 b) {
 static __device__ __noinline__ Fe12 p384_fsqr_call(Fe12 a) {
     Fe12 r;
     P384::fsqr_inline(r.v, a.v);
+    return r;
+}
+static __device__ __noinline__ Fe12 p384_nmul_call(Fe12 a, Fe12 b) {
+    Fe12 r;
+    P384::nmul_inline(r.v, a.v, b.v);
     return r;
 }
 

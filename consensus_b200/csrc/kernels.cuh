@@ -104,6 +104,7 @@ __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restr
     uint32_t run[N];
     C::get_one_n(run);
     int cnt = 0;
+#pragma unroll 1
     for (int k = 0; k < S; k++) {
         uint32_t idx = t + (uint32_t)k * T;
         if (idx >= n) break;
@@ -127,6 +128,7 @@ __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restr
     if (cnt == 0) return;
     uint32_t inv[N];
     n_inv<C>(inv, run);
+#pragma unroll 1
     for (int k = cnt - 1; k >= 0; k--) {
         uint32_t idx = t + (uint32_t)k * T;
         uint32_t w[N], m[N];
