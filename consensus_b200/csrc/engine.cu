@@ -1,7 +1,10 @@
 // engine.cu — host side of libsbv.so: the C ABI of include/sbv.h on top of the sm_100a kernels.
 //
 // One engine owns 1..8 devices of one box.  Every batch is sharded into contiguous ranges, one per
-// device; each device has its own stream, workspace and pinned staging buffer.  No CPU fallback.
+// device.  The host-buffer entry points own a lane (stream + buffers + pinned staging) per call, so two
+// calls overlap; the k_prep -> verify scratch is multi-buffered and event-guarded so launches on different
+// streams overlap too.  With more than one device the packed verdict bitmask is gathered with NCCL
+// (dlopen'd lazily).  No CPU fallback.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 

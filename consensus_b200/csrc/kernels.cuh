@@ -1,13 +1,20 @@
 // kernels.cuh — sm_100a kernels of the sbv hot path (ECDSA verify over NIST prime curves).
 //
-//   k_gtable_init  one-time: affine fixed-base comb table  T[i][b] = b * 2^(GW*i) * G  (Montgomery form; GW = 16 for P-256)
-//   k_prep         per batch: range checks, batched inversion of s mod n (Montgomery's trick, S items
-//                  per thread), u1 = e/s, u2 = r/s, comb bytes of u1 and Booth digits of u2 written
-//                  window-major so the verify kernel reads them coalesced
-//   k_verify       per batch, ONE SIGNATURE PER THREAD: on-curve check, per-thread window table of Q in
-//                  shared memory (bank = lane, so data-dependent indices never conflict), interleaved
-//                  double-and-add for u2*Q, comb adds for u1*G from the L2-resident table, final
-//                  X == r*Z^2 comparison (no inversion)
+//   k_gtable_init        one-time: affine fixed-base comb table  T[i][b] = b * 2^(GW*i) * G  (Montgomery form;
+//                        GW = 16 for P-256: 64 MiB, L2-resident; GW = 8 for P-384)
+//   k_prep               per batch: range checks, batched inversion of s mod n (Montgomery's trick over S items
+//                        per thread, one binary-extended-GCD inversion per thread), u1 = e/s, u2 = r/s, comb
+//                        digits of u1 and Booth digits (or comb bytes) of u2 written window-major so the verify
+//                        kernels read them coalesced
+//   k_verify_coz         keys-per-item path, ONE SIGNATURE PER THREAD: on-curve check, 4-bit signed window over a
+//                        common-Z table of Q (shared memory, bank = lane, + coalesced global scratch), 256
+//                        doublings interleaved with 65 additions, 16 comb additions for u1*G with the next gather
+//                        in flight, final X == r*Z^2 comparison (no inversion)
+//   k_verify             the same with a 3-bit Jacobian window table (A/B variant)
+//   k_keytab_init        registered keys: per-key affine comb table K[k][i][b] = b * 2^(8i) * Q_k
+//   k_verify_keyed       registered-key path, one signature per thread: 32 + 16 comb additions, no doublings
+//   k_verify_keyed_warp  registered-key path, ONE SIGNATURE PER WARP (small batches: lanes add their table points,
+//                        shuffle-tree reduction)
 //
 // Reference boundary: api.Verifier.VerifyConsenterSig / VerifySignature / VerifyRequest
 // (/root/reference/pkg/api/dependencies.go:54-71) — the arithmetic itself is Go crypto/ecdsa
