@@ -61,11 +61,11 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_shard_and_gather():
-    world = 2
+@pytest.mark.parametrize("world", [2, 3])
+def test_multi_rank_shard_and_gather(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29000 + os.getpid() % 2000
+    port = 29000 + (os.getpid() * 7 + world) % 2000
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
