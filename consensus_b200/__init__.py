@@ -22,7 +22,9 @@ SYMBOLS = [
     "sbv_verify_batch_device", "sbv_verify_batch_der", "sbv_sha256_batch", "sbv_hash_verify_batch",
     "sbv_verify_mixed", "sbv_quorum", "sbv_compute_quorum", "sbv_set_keys", "sbv_kernel_launches",
     "sbv_probe_mad_rate", "sbv_profile_enable", "sbv_profile_read", "sbv_verify_registered",
-    "sbv_verify_registered_device", "sbv_hash_verify_registered",
+    "sbv_verify_registered_device", "sbv_hash_verify_registered", "sbv_prepare_quorum", "sbv_verify_quorum",
+    "sbv_comm_unique_id", "sbv_comm_init_rank", "sbv_comm_ranks", "sbv_gather_verdicts_device", "sbv_gather_words_device",
+    "sbv_verify_batch_ranked",
 ]
 
 
@@ -227,6 +229,73 @@ class Engine:
         self._check(self._lib.sbv_verify_mixed(self._h, C.c_size_t(n), _p8(curve_tag), _p8(r48), _p8(s48), _p8(qx48), _p8(qy48),
                                                _p8(digest32), _p8(ok)), "sbv_verify_mixed")
         return ok
+
+    # ---- one process per GPU ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = load_library().sbv_comm_unique_id(buf)
+        if rc != 0:
+            raise EngineFault(f"sbv_comm_unique_id failed ({rc})")
+        return bytes(buf)
+
+    def comm_init_rank(self, uid: bytes, nranks: int, rank: int) -> int:
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        ch = self._lib.sbv_comm_init_rank(self._h, buf, C.c_int(nranks), C.c_int(rank))
+        if ch < 0:
+            self._check(ch, "sbv_comm_init_rank")
+        return ch
+
+    def gather_verdicts_device(self, channel, d_ok, n, d_mask_all, stream=0):
+        vp = C.c_void_p
+        self._check(self._lib.sbv_gather_verdicts_device(self._h, C.c_int(channel), vp(d_ok), C.c_size_t(n), vp(d_mask_all), vp(stream)),
+                    "sbv_gather_verdicts_device")
+
+    def gather_words_device(self, channel, d_all, words, stream=0):
+        vp = C.c_void_p
+        self._check(self._lib.sbv_gather_words_device(self._h, C.c_int(channel), vp(d_all), C.c_size_t(words), vp(stream)), "sbv_gather_words_device")
+
+    def verify_batch_ranked_ptr(self, channel, curve, n, r, s, qx, qy, digest, dlen, ok, mask_all):
+        vp = C.c_void_p
+        self._check(self._lib.sbv_verify_batch_ranked(self._h, C.c_int(channel), C.c_uint8(curve), C.c_size_t(n), vp(r), vp(s), vp(qx), vp(qy),
+                                                      vp(digest), C.c_uint8(dlen), vp(ok), vp(mask_all)), "sbv_verify_batch_ranked")
+
+    def verify_quorum(self, curve, r, s, qx, qy, digest, instance, sender, signer, digest_match, n_instances, threshold, self_id=None):
+        """Commit votes: signatures verified, verdicts counted on the device.  Returns (ok, valid_count, reached)."""
+        r, s, qx, qy, digest, digest_match = map(_u8, (r, s, qx, qy, digest, digest_match))
+        instance = np.ascontiguousarray(instance, dtype=np.uint32)
+        sender = np.ascontiguousarray(sender, dtype=np.uint16)
+        signer = np.ascontiguousarray(signer, dtype=np.uint16)
+        n = instance.size
+        dlen = digest.size // n if n else 32
+        ok = np.zeros(n, np.uint8)
+        cnt = np.zeros(n_instances, np.uint32)
+        reached = np.zeros(n_instances, np.uint8)
+        sid = None
+        if self_id is not None:
+            self_id = np.ascontiguousarray(self_id, dtype=np.uint16)
+            sid = self_id.ctypes.data_as(C.POINTER(C.c_uint16))
+        u16 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint16))
+        self._check(self._lib.sbv_verify_quorum(self._h, C.c_uint8(curve), C.c_size_t(n), _p8(r), _p8(s), _p8(qx), _p8(qy), _p8(digest), C.c_uint8(dlen),
+                                                instance.ctypes.data_as(C.POINTER(C.c_uint32)), u16(sender), u16(signer), _p8(digest_match),
+                                                C.c_size_t(n_instances), sid, C.c_uint32(threshold), _p8(ok),
+                                                cnt.ctypes.data_as(C.POINTER(C.c_uint32)), _p8(reached)), "sbv_verify_quorum")
+        return ok, cnt, reached
+
+    def prepare_quorum(self, instance, sender, digest_match, n_instances, threshold, self_id=None):
+        instance = np.ascontiguousarray(instance, dtype=np.uint32)
+        sender = np.ascontiguousarray(sender, dtype=np.uint16)
+        digest_match = _u8(digest_match)
+        cnt = np.zeros(n_instances, np.uint32)
+        reached = np.zeros(n_instances, np.uint8)
+        sid = None
+        if self_id is not None:
+            self_id = np.ascontiguousarray(self_id, dtype=np.uint16)
+            sid = self_id.ctypes.data_as(C.POINTER(C.c_uint16))
+        self._check(self._lib.sbv_prepare_quorum(self._h, C.c_size_t(instance.size), instance.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                 sender.ctypes.data_as(C.POINTER(C.c_uint16)), _p8(digest_match), C.c_size_t(n_instances), sid,
+                                                 C.c_uint32(threshold), cnt.ctypes.data_as(C.POINTER(C.c_uint32)), _p8(reached)), "sbv_prepare_quorum")
+        return cnt, reached
 
     def quorum(self, instance, sender, signer, digest_match, ok, n_instances, threshold, self_id=None):
         instance = np.ascontiguousarray(instance, dtype=np.uint32)

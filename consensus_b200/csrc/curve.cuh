@@ -40,35 +40,70 @@ struct P256 {
     SBV_DEV static uint32_t p_minus_2_limb(int i) { const uint32_t c[8] = SBV_P256_P_MINUS_2; return c[i]; }
     SBV_DEV static uint32_t n_minus_2_limb(int i) { const uint32_t c[8] = SBV_P256_N_MINUS_2; return c[i]; }
 
-    // T (16 limbs, < p*2^256) -> r = T * 2^-256 mod p, canonical
+    // T (16 limbs, < p*2^256) -> r = T * 2^-256 mod p, canonical.
+    //
+    // U = T + M*p must vanish mod 2^256.  With p = 2^256 - 2^224 + 2^192 + 2^96 - 1 write
+    //   V = T + M*2^96 + M*2^192 - M*2^224,   U = V - M + M*2^256,
+    // so the condition is M = V mod 2^256: limb k of M is limb k of V, and V's limb k only involves limbs < k of
+    // M (the shifts are >= 3 limbs).  Limbs 0..2 of M are T's; the rest fall out of the low ends of the three
+    // shifted chains.  The result is floor(V / 2^256) + M: four term-wise chains over the high half (49
+    // instructions) instead of four digit-wise steps that each ripple to the top limb (72).
     SBV_DEV static void redc(uint32_t (&r)[8], uint32_t (&T)[16]) {
-        uint32_t t16 = 0;
+        const uint32_t m0 = T[0], m1 = T[1], m2 = T[2];
+        uint32_t hi[8], t16;
+        // chain A: + M*2^96 over limbs 3..10, ripple to the top
+        const uint32_t m3 = add_cc(T[3], m0);
+        const uint32_t m4 = addc_cc(T[4], m1);
+        const uint32_t m5 = addc_cc(T[5], m2);
+        const uint32_t a6 = addc_cc(T[6], m3);
+        const uint32_t a7 = addc_cc(T[7], m4);
+        hi[0] = addc_cc(T[8], m5);
+        // limbs 6 and 7 of M also take the low ends of chains B and C; computed here with flag-free arithmetic
+        // (the carry flag of chain A stays live), chains B and C redo those two limbs for their carries
+        const uint32_t m6 = a6 + m0;
+        const uint32_t b7 = a7 + m1 + (m6 < m0 ? 1u : 0u);
+        const uint32_t m7 = b7 - m0;
+        hi[1] = addc_cc(T[9], m6);
+        hi[2] = addc_cc(T[10], m7);
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int b = 2 * k;
-            const uint32_t mlo = T[b], mhi = T[b + 1];
-            T[b + 3] = add_cc(T[b + 3], mlo);
-            T[b + 4] = addc_cc(T[b + 4], mhi);
-            T[b + 5] = addc_cc(T[b + 5], 0);
-            T[b + 6] = addc_cc(T[b + 6], mlo);
-            T[b + 7] = addc_cc(T[b + 7], mhi);
-            T[b + 8] = addc_cc(T[b + 8], mlo);
-            T[b + 9] = addc_cc(T[b + 9], mhi);
-#pragma unroll
-            for (int j = b + 10; j < 16; j++) T[j] = addc_cc(T[j], 0);
-            t16 = addc(t16, 0);
-            T[b + 7] = sub_cc(T[b + 7], mlo);
-            T[b + 8] = subc_cc(T[b + 8], mhi);
-#pragma unroll
-            for (int j = b + 9; j < 16; j++) T[j] = subc_cc(T[j], 0);
-            t16 = subc(t16, 0);
-        }
+        for (int i = 3; i < 8; i++) hi[i] = addc_cc(T[8 + i], 0);
+        t16 = addc(0, 0);
+        // chain B: + M*2^192 over limbs 6..13
+        (void)add_cc(a6, m0);
+        (void)addc_cc(a7, m1);
+        hi[0] = addc_cc(hi[0], m2);
+        hi[1] = addc_cc(hi[1], m3);
+        hi[2] = addc_cc(hi[2], m4);
+        hi[3] = addc_cc(hi[3], m5);
+        hi[4] = addc_cc(hi[4], m6);
+        hi[5] = addc_cc(hi[5], m7);
+        hi[6] = addc_cc(hi[6], 0);
+        hi[7] = addc_cc(hi[7], 0);
+        t16 = addc(t16, 0);
+        // + M*2^256
+        hi[0] = add_cc(hi[0], m0);
+        hi[1] = addc_cc(hi[1], m1);
+        hi[2] = addc_cc(hi[2], m2);
+        hi[3] = addc_cc(hi[3], m3);
+        hi[4] = addc_cc(hi[4], m4);
+        hi[5] = addc_cc(hi[5], m5);
+        hi[6] = addc_cc(hi[6], m6);
+        hi[7] = addc_cc(hi[7], m7);
+        t16 = addc(t16, 0);
+        // chain C: - M*2^224 over limbs 7..14
+        (void)sub_cc(b7, m0);
+        hi[0] = subc_cc(hi[0], m1);
+        hi[1] = subc_cc(hi[1], m2);
+        hi[2] = subc_cc(hi[2], m3);
+        hi[3] = subc_cc(hi[3], m4);
+        hi[4] = subc_cc(hi[4], m5);
+        hi[5] = subc_cc(hi[5], m6);
+        hi[6] = subc_cc(hi[6], m7);
+        hi[7] = subc_cc(hi[7], 0);
+        t16 = subc(t16, 0);
         // result = hi + t16*2^256 < 2p: subtract p iff t16 or hi >= p.  p = (F,1,0,0,0,F,F,F) from the top
         // limb down, so hi >= p is a few logic ops, and the subtraction is one chain with a masked p
         // (no trial subtraction + select).
-        uint32_t hi[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) hi[i] = T[8 + i];
         const uint32_t mid = hi[3] | hi[4] | hi[5];
         const uint32_t low = hi[0] & hi[1] & hi[2];
         // bitwise on 0/1 values: short-circuit && / || would compile to divergent branches

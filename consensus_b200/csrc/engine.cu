@@ -1,13 +1,15 @@
 // engine.cu — host side of libsbv.so: the C ABI of include/sbv.h on top of the sm_100a kernels.
 //
-// One engine owns 1..8 devices of one box.  Every batch is sharded into contiguous ranges, one per
-// device.  The host-buffer entry points own a lane (stream + buffers + pinned staging) per call, so two
-// calls overlap; the k_prep -> verify scratch is multi-buffered and event-guarded so launches on different
-// streams overlap too.  With more than one device the packed verdict bitmask is gathered with NCCL
+// One engine owns 1..8 devices of one box (single process), or is one RANK of a one-process-per-GPU deployment
+// (sbv_comm_init_rank).  Every batch is sharded into contiguous ranges, one per device.  Every host-buffer entry point
+// owns a lane (stream + buffers + pinned staging) per call, so up to SBV_LANES calls overlap; the per-launch scratch of
+// the verify pipeline (pipeline.cu) is multi-buffered and event-guarded so launches on different streams overlap too.
+// The only exchange between devices / ranks is the all-gather of packed verdict (and quorum) bitmasks, with NCCL
 // (dlopen'd lazily).  No CPU fallback.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -31,118 +33,10 @@ int env_int(const char *name, int dflt) {
 
 size_t fbytes(uint8_t curve) { return curve == SBV_P256 ? 32 : 48; }
 
-int ensure_workspace(sbv_engine *e, Dev &d, size_t n) {
-    if (n <= d.cap) return 0;
-    size_t cap = n + n / 8 + 1024;
-    CU(e, cudaSetDevice(d.ordinal));
-    uint8_t **ptrs[] = {&d.d_r, &d.d_s, &d.d_qx, &d.d_qy, &d.d_dig, &d.d_ok};
-    CU(e, cudaDeviceSynchronize());  // nothing may still be using the old scratch
-    for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
-    for (auto &w : d.ws) {
-        if (w.gidx) cudaFree(w.gidx);
-        if (w.digits) cudaFree(w.digits);
-        if (w.flags) cudaFree(w.flags);
-        if (w.tscr) cudaFree(w.tscr);
-        w.tscr = nullptr;
-        w.gidx = nullptr; w.digits = nullptr; w.flags = nullptr; w.used = false;
-        if (!w.done) CU(e, cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
-    }
-    CU(e, cudaMalloc(&d.d_r, cap * 48));
-    CU(e, cudaMalloc(&d.d_s, cap * 48));
-    CU(e, cudaMalloc(&d.d_qx, cap * 48));
-    CU(e, cudaMalloc(&d.d_qy, cap * 48));
-    CU(e, cudaMalloc(&d.d_dig, cap * 64));
-    CU(e, cudaMalloc(&d.d_ok, cap));
-    for (auto &w : d.ws) {
-        CU(e, cudaMalloc(&w.gidx, cap * 48 * sizeof(uint16_t)));
-        CU(e, cudaMalloc(&w.flags, cap));
-        CU(e, cudaMalloc(&w.digits, cap * 132));
-        CU(e, cudaMalloc(&w.tscr, cap * 12 * 12 * sizeof(uint32_t)));  // 12N words per signature, N = 12 for P-384
-    }
-    d.cap = cap;
-    return 0;
-}
-
-int ensure_pinned(sbv_engine *e, Dev &d, size_t bytes) {
-    if (bytes <= d.h_pin_cap) return 0;
-    CU(e, cudaSetDevice(d.ordinal));
-    if (d.h_pin) cudaFreeHost(d.h_pin);
-    d.h_pin = nullptr;
-    size_t cap = bytes + bytes / 4 + 4096;
-    CU(e, cudaHostAlloc(&d.h_pin, cap, cudaHostAllocPortable));
-    d.h_pin_cap = cap;
-    return 0;
-}
-
-int ensure_scratch(sbv_engine *e, Dev &d, size_t bytes) { return sbv_ensure_scratch(e, d, bytes); }
-}  // namespace
-int sbv_ensure_scratch(sbv_engine *e, Dev &d, size_t bytes) {
-    if (bytes <= d.scratch_cap) return 0;
-    CU(e, cudaSetDevice(d.ordinal));
-    if (d.d_scratch) cudaFree(d.d_scratch);
-    d.d_scratch = nullptr;
-    size_t cap = bytes + bytes / 4 + 4096;
-    CU(e, cudaMalloc(&d.d_scratch, cap));
-    d.scratch_cap = cap;
-    return 0;
-}
-namespace {
-
-int ensure_msgs(sbv_engine *e, Dev &d, size_t bytes, size_t n_off) {
-    CU(e, cudaSetDevice(d.ordinal));
-    if (bytes > d.msg_cap) {
-        if (d.d_msgs) cudaFree(d.d_msgs);
-        d.d_msgs = nullptr;
-        size_t cap = bytes + bytes / 8 + 4096;
-        CU(e, cudaMalloc(&d.d_msgs, cap));
-        d.msg_cap = cap;
-    }
-    if (n_off > d.off_cap) {
-        if (d.d_off) cudaFree(d.d_off);
-        d.d_off = nullptr;
-        size_t cap = n_off + n_off / 8 + 1024;
-        CU(e, cudaMalloc(&d.d_off, cap * sizeof(uint64_t)));
-        if (d.d_perm) cudaFree(d.d_perm);
-        d.d_perm = nullptr;
-        CU(e, cudaMalloc(&d.d_perm, (cap + 3 * 1024) * sizeof(uint32_t)));
-        d.off_cap = cap;
-    }
-    return 0;
-}
-
 bool is_pinned(const void *p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
-}
-
-// H2D of a caller buffer: direct when pinned, else through the device's pinned staging area at
-// offset `stage_off` (caller guarantees the staging area is large enough and not reused until the
-// stream has drained).
-int h2d(sbv_engine *e, Dev &d, void *dst, const void *src, size_t bytes, size_t &stage_off, cudaStream_t st) {
-    if (bytes == 0) return 0;
-    if (is_pinned(src)) {
-        CU(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
-    } else {
-        memcpy(d.h_pin + stage_off, src, bytes);
-        CU(e, cudaMemcpyAsync(dst, d.h_pin + stage_off, bytes, cudaMemcpyHostToDevice, st));
-        stage_off += (bytes + 255) & ~(size_t)255;
-    }
-    return 0;
-}
-
-// inputs on device d; enqueues on st; no sync
-int launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_r, const uint8_t *d_s,
-                  const uint8_t *d_qx, const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok,
-                  cudaStream_t st) {
-    if (n == 0) return 0;
-    if (curve == SBV_P256) {
-        if (e->p256_variant == 2) return sbv_launch_p256_coz_b448(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
-        if (e->p256_variant == 1) return sbv_launch_p256_coz_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
-        return sbv_launch_p256_w3_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
-    }
-    if (e->p384_variant == 1) return sbv_launch_p384_coz_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
-    return sbv_launch_p384_w3_b64(e, d, n, d_r, d_s, d_qx, d_qy, d_dig, dlen, d_ok, st);
 }
 
 __global__ void k_mad_probe(uint32_t *out, uint32_t iters) {
@@ -161,13 +55,28 @@ __global__ void k_mad_probe(uint32_t *out, uint32_t iters) {
     if (s == 0x1234567) out[0] = (uint32_t)s;
 }
 
-
 }  // namespace
-int sbv_ensure_workspace(sbv_engine *e, Dev &d, size_t n) { return ensure_workspace(e, d, n); }
+
+int sbv_ensure_scratch(sbv_engine *e, Dev &d, size_t bytes) {
+    if (bytes <= d.scratch_cap) return 0;
+    CU(e, cudaSetDevice(d.ordinal));
+    if (d.d_scratch) cudaFree(d.d_scratch);
+    d.d_scratch = nullptr;
+    d.scratch_cap = 0;
+    size_t cap = bytes + bytes / 4 + 4096;
+    CU(e, cudaMalloc(&d.d_scratch, cap));
+    d.scratch_cap = cap;
+    return 0;
+}
+
 int sbv_lane_acquire(sbv_engine *e) {
     std::unique_lock<std::mutex> lk(e->mu);
-    e->lane_cv.wait(lk, [&] { return !e->lane_busy[0] || !e->lane_busy[1]; });
-    int lane = e->lane_busy[0] ? 1 : 0;
+    int lane = -1;
+    e->lane_cv.wait(lk, [&] {
+        for (int i = 0; i < SBV_LANES; i++)
+            if (!e->lane_busy[i]) { lane = i; return true; }
+        return false;
+    });
     e->lane_busy[lane] = true;
     return lane;
 }
@@ -184,6 +93,7 @@ int sbv_lane_ensure(sbv_engine *e, Dev &d, Dev::Lane &ln, size_t n, size_t pinne
         for (auto p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
         if (ln.d_slot) cudaFree(ln.d_slot);
         ln.d_slot = nullptr;
+        ln.cap = 0;
         const size_t cap = n + n / 8 + 1024;
         CU(e, cudaMalloc(&ln.d_r, cap * 48));
         CU(e, cudaMalloc(&ln.d_s, cap * 48));
@@ -198,6 +108,7 @@ int sbv_lane_ensure(sbv_engine *e, Dev &d, Dev::Lane &ln, size_t n, size_t pinne
         CU(e, cudaStreamSynchronize(ln.stream));
         if (ln.h_pin) cudaFreeHost(ln.h_pin);
         ln.h_pin = nullptr;
+        ln.h_pin_cap = 0;
         const size_t cap = pinned_bytes + pinned_bytes / 4 + 4096;
         CU(e, cudaHostAlloc(&ln.h_pin, cap, cudaHostAllocPortable));
         ln.h_pin_cap = cap;
@@ -206,10 +117,12 @@ int sbv_lane_ensure(sbv_engine *e, Dev &d, Dev::Lane &ln, size_t n, size_t pinne
     return 0;
 }
 int sbv_lane_ensure_msgs(sbv_engine *e, Dev::Lane &ln, size_t bytes, size_t n_off) {
+    if (!ln.stream) CU(e, cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
     if (bytes > ln.msg_cap) {
         CU(e, cudaStreamSynchronize(ln.stream));
         if (ln.d_msgs) cudaFree(ln.d_msgs);
         ln.d_msgs = nullptr;
+        ln.msg_cap = 0;
         const size_t cap = bytes + bytes / 8 + 4096;
         CU(e, cudaMalloc(&ln.d_msgs, cap));
         ln.msg_cap = cap;
@@ -217,14 +130,28 @@ int sbv_lane_ensure_msgs(sbv_engine *e, Dev::Lane &ln, size_t bytes, size_t n_of
     if (n_off > ln.off_cap) {
         CU(e, cudaStreamSynchronize(ln.stream));
         if (ln.d_off) cudaFree(ln.d_off);
+        if (ln.d_perm) cudaFree(ln.d_perm);
         ln.d_off = nullptr;
+        ln.d_perm = nullptr;
+        ln.off_cap = 0;
         const size_t cap = n_off + n_off / 8 + 1024;
         CU(e, cudaMalloc(&ln.d_off, cap * sizeof(uint64_t)));
-        if (ln.d_perm) cudaFree(ln.d_perm);
-        ln.d_perm = nullptr;
         CU(e, cudaMalloc(&ln.d_perm, (cap + 3 * 1024) * sizeof(uint32_t)));
         ln.off_cap = cap;
     }
+    return 0;
+}
+int sbv_lane_ensure_aux(sbv_engine *e, Dev::Lane &ln, size_t bytes) {
+    if (!ln.stream) CU(e, cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+    if (bytes <= ln.aux_cap) return 0;
+    CU(e, cudaStreamSynchronize(ln.stream));
+    if (ln.d_aux) cudaFree(ln.d_aux);
+    if (ln.h_aux) cudaFreeHost(ln.h_aux);
+    ln.d_aux = nullptr; ln.h_aux = nullptr; ln.aux_cap = 0;
+    const size_t cap = bytes + bytes / 4 + 4096;
+    CU(e, cudaMalloc(&ln.d_aux, cap));
+    CU(e, cudaHostAlloc(&ln.h_aux, cap, cudaHostAllocPortable));
+    ln.aux_cap = cap;
     return 0;
 }
 int sbv_launch_sha256(sbv_engine *e, size_t n, const uint8_t *d_msgs, const uint64_t *d_off, uint64_t base, uint8_t *d_digest, uint32_t *d_perm,
@@ -244,57 +171,63 @@ int sbv_launch_sha256(sbv_engine *e, size_t n, const uint8_t *d_msgs, const uint
     CU(e, cudaGetLastError());
     return 0;
 }
+// H2D of a caller buffer on the lane's stream: direct when pinned, else through the lane's pinned staging area at offset
+// `stage_off` (the caller sized it and does not reuse it until the stream has drained).
 int sbv_lane_h2d(sbv_engine *e, Dev::Lane &ln, void *dst, const void *src, size_t bytes, size_t &stage_off) {
     if (bytes == 0) return 0;
     if (is_pinned(src)) {
         CU(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ln.stream));
     } else {
+        if (stage_off + bytes > ln.h_pin_cap) return fail(e, SBV_ERR_NOMEM, "pinned staging area too small (%zu + %zu > %zu)", stage_off, bytes, ln.h_pin_cap);
         memcpy(ln.h_pin + stage_off, src, bytes);
         CU(e, cudaMemcpyAsync(dst, ln.h_pin + stage_off, bytes, cudaMemcpyHostToDevice, ln.stream));
         stage_off += (bytes + 255) & ~(size_t)255;
     }
     return 0;
 }
-int sbv_take_scratch(sbv_engine *e, Dev &d, cudaStream_t st, Dev::Scratch **out) {
-    Dev::Scratch &w = d.ws[d.ws_next++ & 3];
-    if (w.used) CU(e, cudaStreamWaitEvent(st, w.done, 0));
-    w.used = true;
-    *out = &w;
-    return 0;
-}
-int sbv_ensure_pinned(sbv_engine *e, Dev &d, size_t bytes) { return ensure_pinned(e, d, bytes); }
-int sbv_h2d(sbv_engine *e, Dev &d, void *dst, const void *src, size_t bytes, size_t &stage_off, cudaStream_t st) { return h2d(e, d, dst, src, bytes, stage_off, st); }
+
 namespace {
 
-// ---- NCCL, loaded with dlopen only by multi-device engines ----
+// ---- NCCL, loaded with dlopen only by multi-device / multi-rank engines ----
+struct NcclUniqueId { char internal[128]; };
 typedef int (*nccl_comm_init_all_t)(void **comms, int ndev, const int *devlist);
+typedef int (*nccl_comm_init_rank_t)(void **comm, int nranks, NcclUniqueId id, int rank);
+typedef int (*nccl_get_unique_id_t)(NcclUniqueId *id);
 typedef int (*nccl_comm_destroy_t)(void *comm);
 typedef int (*nccl_group_t)(void);
 typedef int (*nccl_all_gather_t)(const void *send, void *recv, size_t count, int dtype, void *comm, cudaStream_t st);
 typedef const char *(*nccl_err_t)(int);
 struct NcclApi {
+    void *lib = nullptr;
     nccl_comm_init_all_t comm_init_all = nullptr;
+    nccl_comm_init_rank_t comm_init_rank = nullptr;
+    nccl_get_unique_id_t get_unique_id = nullptr;
     nccl_comm_destroy_t comm_destroy = nullptr;
     nccl_group_t group_start = nullptr, group_end = nullptr;
     nccl_all_gather_t all_gather = nullptr;
     nccl_err_t err_string = nullptr;
 } g_nccl;
+std::mutex g_nccl_mu;
 constexpr int NCCL_UINT32 = 3;  // ncclUint32
 
 int nccl_load(sbv_engine *e) {
-    if (e->nccl_lib) return 0;
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.lib) return 0;
     void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
     if (!h) return fail(e, SBV_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
     g_nccl.comm_init_all = (nccl_comm_init_all_t)dlsym(h, "ncclCommInitAll");
+    g_nccl.comm_init_rank = (nccl_comm_init_rank_t)dlsym(h, "ncclCommInitRank");
+    g_nccl.get_unique_id = (nccl_get_unique_id_t)dlsym(h, "ncclGetUniqueId");
     g_nccl.comm_destroy = (nccl_comm_destroy_t)dlsym(h, "ncclCommDestroy");
     g_nccl.group_start = (nccl_group_t)dlsym(h, "ncclGroupStart");
     g_nccl.group_end = (nccl_group_t)dlsym(h, "ncclGroupEnd");
     g_nccl.all_gather = (nccl_all_gather_t)dlsym(h, "ncclAllGather");
     g_nccl.err_string = (nccl_err_t)dlsym(h, "ncclGetErrorString");
-    if (!g_nccl.comm_init_all || !g_nccl.comm_destroy || !g_nccl.group_start || !g_nccl.group_end || !g_nccl.all_gather)
+    if (!g_nccl.comm_init_all || !g_nccl.comm_init_rank || !g_nccl.get_unique_id || !g_nccl.comm_destroy || !g_nccl.group_start ||
+        !g_nccl.group_end || !g_nccl.all_gather)
         return fail(e, SBV_ERR_NCCL, "libnccl lacks a required symbol");
-    e->nccl_lib = h;
+    g_nccl.lib = h;
     return 0;
 }
 #define NC(e, call)                                                                                       \
@@ -310,55 +243,88 @@ Shard shard_of(size_t n, int g, int G) {
     return {lo, hi - lo};
 }
 
-
-// Multi-device epilogue: every device packs its shard's verdict bytes into a bitmask
-// (k_pack_bits), one ncclAllGather (in place, on each device's compute stream, right behind its
-// verify kernel) assembles the whole mask on every device, and device 0 returns it to the host in
-// a single n/8-byte copy.  Shards are padded to a common word count, so device g's words start at
-// g * words_per.
+// Multi-device epilogue: every device packs its shard's verdict bytes into a bitmask (k_pack_bits), one ncclAllGather
+// (in place, on each device's lane stream, right behind its verify kernel) assembles the whole mask on every device,
+// and device 0 returns it to the host in a single n/8-byte copy into the lane's pinned mirror.  Shards are padded to a
+// common word count, so device g's words start at g * words_per.  `extra_words` more words per device travel in the
+// same collective (the quorum path appends its `reached` bits).
 size_t words_per_shard(size_t n, int G) { return (((n + G - 1) / G) + 31) / 32; }
 
-int gather_verdicts(sbv_engine *e, size_t n, int lane) {
+int gather_verdicts(sbv_engine *e, size_t n, int lane, size_t extra_words) {
     const int G = (int)e->devs.size();
-    const size_t wp = words_per_shard(n, G);
+    const size_t wp = words_per_shard(n, G) + extra_words;
     for (int g = 0; g < G; g++) {
         Dev &d = e->devs[g];
         CU(e, cudaSetDevice(d.ordinal));
-        int rc = sbv_ensure_scratch(e, d, wp * G * 4);
+        Dev::Lane &ln = d.lanes[lane];
+        int rc = sbv_lane_ensure_aux(e, ln, wp * G * 4);
         if (rc) return rc;
+    }
+    for (int g = 0; g < G; g++) {
+        Dev &d = e->devs[g];
+        CU(e, cudaSetDevice(d.ordinal));
         Shard sh = shard_of(n, g, G);
         Dev::Lane &ln = d.lanes[lane];
-        if (!ln.stream) CU(e, cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
-        uint32_t *mine = (uint32_t *)d.d_scratch + wp * g;
-        CU(e, cudaMemsetAsync(mine, 0, wp * 4, ln.stream));
+        uint32_t *mine = (uint32_t *)ln.d_aux + wp * g;
+        CU(e, cudaMemsetAsync(mine, 0, (wp - extra_words) * 4, ln.stream));
         if (sh.n) {
             k_pack_bits<<<(uint32_t)((sh.n + 255) / 256), 256, 0, ln.stream>>>((uint32_t)sh.n, ln.d_ok, mine);
             e->launches += 1;
             CU(e, cudaGetLastError());
         }
     }
-    NC(e, g_nccl.group_start());
-    for (int g = 0; g < G; g++) {
-        Dev &d = e->devs[g];
-        uint32_t *buf = (uint32_t *)d.d_scratch;
-        NC(e, g_nccl.all_gather(buf + wp * g, buf, wp, NCCL_UINT32, e->nccl_comms[g], d.lanes[lane].stream));
+    {
+        std::lock_guard<std::mutex> lk(e->mu);  // collectives of one communicator set must be issued in one order
+        NC(e, g_nccl.group_start());
+        for (int g = 0; g < G; g++) {
+            Dev &d = e->devs[g];
+            uint32_t *buf = (uint32_t *)d.lanes[lane].d_aux;
+            NC(e, g_nccl.all_gather(buf + wp * g, buf, wp, NCCL_UINT32, e->nccl_comms[g], d.lanes[lane].stream));
+        }
+        NC(e, g_nccl.group_end());
     }
-    NC(e, g_nccl.group_end());
     Dev &d0 = e->devs[0];
     CU(e, cudaSetDevice(d0.ordinal));
-    e->gather_words.resize(wp * G);
-    CU(e, cudaMemcpyAsync(e->gather_words.data(), d0.d_scratch, wp * G * 4, cudaMemcpyDeviceToHost, d0.lanes[lane].stream));
+    CU(e, cudaMemcpyAsync(d0.lanes[lane].h_aux, d0.lanes[lane].d_aux, wp * G * 4, cudaMemcpyDeviceToHost, d0.lanes[lane].stream));
     return 0;
 }
 
-void unpack_verdicts(sbv_engine *e, size_t n, uint8_t *ok_host) {
+void unpack_verdicts(sbv_engine *e, size_t n, int lane, size_t extra_words, uint8_t *ok_host) {
     const int G = (int)e->devs.size();
-    const size_t wp = words_per_shard(n, G);
+    const size_t wp = words_per_shard(n, G) + extra_words;
+    const uint32_t *words = (const uint32_t *)e->devs[0].lanes[lane].h_aux;
     for (int g = 0; g < G; g++) {
         Shard sh = shard_of(n, g, G);
-        const uint32_t *w = e->gather_words.data() + wp * g;
+        const uint32_t *w = words + wp * g;
         for (size_t i = 0; i < sh.n; i++) ok_host[sh.lo + i] = (w[i >> 5] >> (i & 31)) & 1u;
     }
+}
+
+int sync_lane(sbv_engine *e, int lane) {
+    for (Dev &d : e->devs) {
+        if (!d.lanes[lane].stream) continue;
+        CU(e, cudaSetDevice(d.ordinal));
+        CU(e, cudaStreamSynchronize(d.lanes[lane].stream));
+    }
+    return 0;
+}
+
+// stages the five field arrays of items [lo, lo+cnt) on device d's lane and enqueues the verify pipeline
+int stage_and_verify(sbv_engine *e, Dev &d, int lane, uint8_t curve, size_t lo, size_t cnt, const uint8_t *r, const uint8_t *s, const uint8_t *qx,
+                     const uint8_t *qy, const uint8_t *digest, uint8_t digest_len) {
+    const size_t L = fbytes(curve);
+    Dev::Lane &ln = d.lanes[lane];
+    CU(e, cudaSetDevice(d.ordinal));
+    int rc = sbv_lane_ensure(e, d, ln, cnt, cnt * (4 * L + digest_len + 1) + 8 * 256);
+    if (rc) return rc;
+    size_t so = 0;
+    if ((rc = sbv_lane_h2d(e, ln, ln.d_r, r + lo * L, cnt * L, so))) return rc;
+    if ((rc = sbv_lane_h2d(e, ln, ln.d_s, s + lo * L, cnt * L, so))) return rc;
+    if ((rc = sbv_lane_h2d(e, ln, ln.d_dig, digest + lo * digest_len, cnt * digest_len, so))) return rc;
+    if ((rc = sbv_lane_h2d(e, ln, ln.d_qx, qx + lo * L, cnt * L, so))) return rc;
+    if ((rc = sbv_lane_h2d(e, ln, ln.d_qy, qy + lo * L, cnt * L, so))) return rc;
+    std::lock_guard<std::mutex> lk(e->mu);
+    return sbv_launch_verify(e, d, curve, cnt, ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, digest_len, ln.d_ok, ln.stream);
 }
 
 }  // namespace
@@ -372,9 +338,16 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count < n_devices) return SBV_ERR_CUDA;
     sbv_engine *e = new sbv_engine();
-    e->p256_variant = env_int("SBV_P256_VARIANT", 1);
-    e->p384_variant = env_int("SBV_P384_VARIANT", 1);
     e->keyed_warp_limit = env_int("SBV_KEYED_WARP_LIMIT", 2048);
+    e->group_threshold = env_int("SBV_GROUP_THRESHOLD", 16);
+    e->group_max_keys = env_int("SBV_GROUP_MAX_KEYS", 8192);
+    {
+        // per-engine hash seed: an adversary who picks the keys of a batch cannot aim at the probe sequence
+        uint64_t t = (uint64_t)(uintptr_t)e;
+        FILE *f = fopen("/dev/urandom", "rb");
+        if (f) { if (fread(&t, sizeof t, 1, f) != 1) t ^= 0x9e3779b97f4a7c15ull; fclose(f); }
+        e->hash_seed = (uint32_t)(t ^ (t >> 32)) | 1u;
+    }
     e->devs.resize(n_devices);
     for (int g = 0; g < n_devices; g++) {
         Dev &d = e->devs[g];
@@ -383,7 +356,7 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
         if (st == cudaSuccess) st = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
         if (st == cudaSuccess && sbv_init_gtables(e, d) != 0) st = cudaErrorUnknown;
         if (st != cudaSuccess) {
-            fprintf(stderr, "sbv_create: device %d: %s\n", d.ordinal, cudaGetErrorString(st));
+            fprintf(stderr, "sbv_create: device %d: %s (%s)\n", d.ordinal, cudaGetErrorString(st), e->err.c_str());
             sbv_destroy(e);
             return SBV_ERR_CUDA;
         }
@@ -405,34 +378,45 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
 
 void sbv_destroy(sbv_engine *e) {
     if (!e) return;
-    for (void *c : e->nccl_comms) if (c && g_nccl.comm_destroy) g_nccl.comm_destroy(c);
     for (Dev &d : e->devs) {
         cudaSetDevice(d.ordinal);
-        if (d.stream) cudaStreamSynchronize(d.stream);
-        void *ptrs[] = {d.gtab[0], d.gtab[1], d.d_r, d.d_s, d.d_qx, d.d_qy, d.d_dig, d.d_ok,  d.d_msgs, d.d_off, d.d_perm, d.d_scratch};
-        for (auto &w : d.ws) {
-            void *wp[] = {w.gidx, w.flags, w.digits, w.tscr};
-            for (void *p : wp) if (p) cudaFree(p);
-            if (w.done) cudaEventDestroy(w.done);
-        }
+        cudaDeviceSynchronize();
+    }
+    for (void *c : e->nccl_comms) if (c && g_nccl.comm_destroy) g_nccl.comm_destroy(c);
+    for (void *c : e->rank_comms) if (c && g_nccl.comm_destroy) g_nccl.comm_destroy(c);
+    for (Dev &d : e->devs) {
+        cudaSetDevice(d.ordinal);
+        void *ptrs[] = {d.gtab[0], d.gtab[1], d.d_scratch};
         for (void *p : ptrs) if (p) cudaFree(p);
+        sbv_scratch_free(d);
         sbv_keys_free(d);
         for (auto &ln : d.lanes) {
-            if (ln.stream) cudaStreamSynchronize(ln.stream);
-            void *lp[] = {ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, ln.d_ok, ln.d_slot, ln.d_msgs, ln.d_off, ln.d_perm};
+            void *lp[] = {ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, ln.d_ok, ln.d_slot, ln.d_msgs, ln.d_off, ln.d_perm, ln.d_aux};
             for (void *p : lp) if (p) cudaFree(p);
             if (ln.h_pin) cudaFreeHost(ln.h_pin);
+            if (ln.h_aux) cudaFreeHost(ln.h_aux);
             if (ln.stream) cudaStreamDestroy(ln.stream);
+            if (ln.stream2) cudaStreamDestroy(ln.stream2);
+            if (ln.ev_a) cudaEventDestroy(ln.ev_a);
+            if (ln.ev_b) cudaEventDestroy(ln.ev_b);
         }
-        if (d.h_pin) cudaFreeHost(d.h_pin);
+        for (cudaEvent_t ev : d.prof_events) cudaEventDestroy(ev);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     delete e;
 }
 
-const char *sbv_last_error(const sbv_engine *e) { return e ? e->err.c_str() : "null engine"; }
+// Copies the description of the last fault into a thread-local buffer: valid until this thread's next call.
+const char *sbv_last_error(const sbv_engine *e) {
+    static thread_local std::string copy;
+    if (!e) return "null engine";
+    sbv_engine *m = const_cast<sbv_engine *>(e);
+    std::lock_guard<std::mutex> lk(m->err_mu);
+    copy = m->err;
+    return copy.c_str();
+}
 int sbv_device_count(const sbv_engine *e) { return e ? (int)e->devs.size() : 0; }
-uint64_t sbv_kernel_launches(const sbv_engine *e) { return e ? e->launches : 0; }
+uint64_t sbv_kernel_launches(const sbv_engine *e) { return e ? e->launches.load() : 0; }
 
 void sbv_compute_quorum(uint64_t n, uint32_t *q, uint32_t *f) {
     // f = (n-1)/3 ; q = ceil((n+f+1)/2) — util.go:183-187, exact in integers
@@ -447,40 +431,13 @@ int sbv_verify_batch_device(sbv_engine *e, int device_index, uint8_t curve, size
     if (!e || curve > SBV_P384 || device_index < 0 || device_index >= (int)e->devs.size() || digest_len == 0)
         return fail(e, SBV_ERR_ARG, "sbv_verify_batch_device: bad argument");
     if (n == 0) return SBV_OK;
-    if (n > 0x7fffffffu || (digest_len & 3)) return fail(e, SBV_ERR_ARG, "n too large or digest_len not a multiple of 4");
+    if (n > 0x7fffffffu || (digest_len & 3) || digest_len > 64) return fail(e, SBV_ERR_ARG, "n too large or digest_len not a multiple of 4");
+    if (!d_r || !d_s || !d_qx || !d_qy || !d_digest || !d_ok) return fail(e, SBV_ERR_ARG, "null buffer");
     std::lock_guard<std::mutex> lk(e->mu);
     Dev &d = e->devs[device_index];
     CU(e, cudaSetDevice(d.ordinal));
-    int rc = ensure_workspace(e, d, n);
-    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;  // NULL = the legacy default stream
-    return launch_verify(e, d, curve, n, d_r, d_s, d_qx, d_qy, d_digest, digest_len, d_ok, st);
-}
-
-// Enqueues H2D, both kernels and the verdict D2H of items [lo, lo + cnt) of a single-device call on
-// lane `lane` (no synchronisation).
-static int enqueue_range_1dev(sbv_engine *e, int lane, uint8_t curve, size_t lo, size_t cnt, const uint8_t *r, const uint8_t *s,
-                              const uint8_t *qx, const uint8_t *qy, const uint8_t *digest, uint8_t digest_len, uint8_t *ok) {
-    const size_t L = fbytes(curve);
-    Dev &d = e->devs[0];
-    Dev::Lane &ln = d.lanes[lane];
-    CU(e, cudaSetDevice(d.ordinal));
-    int rc = sbv_lane_ensure(e, d, ln, cnt, cnt * (4 * L + digest_len + 1) + 8 * 256);
-    if (rc) return rc;
-    size_t so = 0;
-    if ((rc = sbv_lane_h2d(e, ln, ln.d_r, r + lo * L, cnt * L, so))) return rc;
-    if ((rc = sbv_lane_h2d(e, ln, ln.d_s, s + lo * L, cnt * L, so))) return rc;
-    if ((rc = sbv_lane_h2d(e, ln, ln.d_dig, digest + lo * digest_len, cnt * digest_len, so))) return rc;
-    if ((rc = sbv_lane_h2d(e, ln, ln.d_qx, qx + lo * L, cnt * L, so))) return rc;
-    if ((rc = sbv_lane_h2d(e, ln, ln.d_qy, qy + lo * L, cnt * L, so))) return rc;
-    {
-        std::lock_guard<std::mutex> lk(e->mu);
-        rc = ensure_workspace(e, d, cnt);
-        if (!rc) rc = launch_verify(e, d, curve, cnt, ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, digest_len, ln.d_ok, ln.stream);
-    }
-    if (rc) return rc;
-    CU(e, cudaMemcpyAsync(ok + lo, ln.d_ok, cnt, cudaMemcpyDeviceToHost, ln.stream));
-    return 0;
+    return sbv_launch_verify(e, d, curve, n, d_r, d_s, d_qx, d_qy, d_digest, digest_len, d_ok, st);
 }
 
 int sbv_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *r, const uint8_t *s, const uint8_t *qx,
@@ -490,52 +447,115 @@ int sbv_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *r, c
     if (n == 0) return SBV_OK;
     if (!r || !s || !qx || !qy || !digest || !ok) return fail(e, SBV_ERR_ARG, "null buffer");
     if (n > 0x7fffffffu) return fail(e, SBV_ERR_ARG, "n too large");
-    const size_t L = fbytes(curve);
     const int G = (int)e->devs.size();
     // A call owns one lane (stream + buffers) on every device; the engine lock is held only while
-    // kernels are enqueued, so a second host thread overlaps its copies and kernels with ours.
-    const int lane = sbv_lane_acquire(e);
-    struct Release { sbv_engine *e; int lane; ~Release() { if (lane >= 0) sbv_lane_release(e, lane); } } release{e, lane};
+    // kernels are enqueued, so other host threads overlap their copies and kernels with ours.
+    LaneGuard guard(e);
+    const int lane = guard.lane;
     if (G == 1) {
-        // (Splitting one call over both lanes was measured: no gain for one caller — the two half-size
-        // verify kernels share the SMs like one launch — and it serialises two concurrent callers.)
-        int rc = enqueue_range_1dev(e, lane, curve, 0, n, r, s, qx, qy, digest, digest_len, ok);
+        Dev &d = e->devs[0];
+        int rc = stage_and_verify(e, d, lane, curve, 0, n, r, s, qx, qy, digest, digest_len);
         if (rc) return rc;
-        CU(e, cudaStreamSynchronize(e->devs[0].lanes[lane].stream));
-        return SBV_OK;
+        CU(e, cudaMemcpyAsync(ok, d.lanes[lane].d_ok, n, cudaMemcpyDeviceToHost, d.lanes[lane].stream));
+        return sync_lane(e, lane);
     }
     for (int g = 0; g < G; g++) {
-        Dev &d = e->devs[g];
-        Dev::Lane &ln = d.lanes[lane];
         Shard sh = shard_of(n, g, G);
         if (sh.n == 0) continue;
-        CU(e, cudaSetDevice(d.ordinal));
-        int rc = sbv_lane_ensure(e, d, ln, sh.n, sh.n * (4 * L + digest_len + 1) + 8 * 256);
-        if (rc) return rc;
-        size_t so = 0;
-        if ((rc = sbv_lane_h2d(e, ln, ln.d_r, r + sh.lo * L, sh.n * L, so))) return rc;
-        if ((rc = sbv_lane_h2d(e, ln, ln.d_s, s + sh.lo * L, sh.n * L, so))) return rc;
-        if ((rc = sbv_lane_h2d(e, ln, ln.d_dig, digest + sh.lo * digest_len, sh.n * digest_len, so))) return rc;
-        if ((rc = sbv_lane_h2d(e, ln, ln.d_qx, qx + sh.lo * L, sh.n * L, so))) return rc;
-        if ((rc = sbv_lane_h2d(e, ln, ln.d_qy, qy + sh.lo * L, sh.n * L, so))) return rc;
-        {
-            std::lock_guard<std::mutex> lk(e->mu);
-            rc = ensure_workspace(e, d, sh.n);
-            if (!rc) rc = launch_verify(e, d, curve, sh.n, ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, digest_len, ln.d_ok, ln.stream);
-        }
+        int rc = stage_and_verify(e, e->devs[g], lane, curve, sh.lo, sh.n, r, s, qx, qy, digest, digest_len);
         if (rc) return rc;
     }
-    {
-        std::lock_guard<std::mutex> lk(e->mu);  // the gather buffers are per device, not per lane
-        int rc = gather_verdicts(e, n, lane);
-        if (rc) return rc;
-        for (int g = 0; g < G; g++) {
-            CU(e, cudaSetDevice(e->devs[g].ordinal));
-            CU(e, cudaStreamSynchronize(e->devs[g].lanes[lane].stream));
-        }
-        unpack_verdicts(e, n, ok);
+    int rc = gather_verdicts(e, n, lane, 0);
+    if (rc) return rc;
+    if ((rc = sync_lane(e, lane))) return rc;
+    unpack_verdicts(e, n, lane, 0, ok);
+    return SBV_OK;
+}
+
+// ---- one process per GPU: this engine is one rank of an N-rank job ------------------------------------------
+int sbv_comm_unique_id(uint8_t *id128) {
+    if (!id128) return SBV_ERR_ARG;
+    if (nccl_load(nullptr) != 0) return SBV_ERR_NCCL;
+    NcclUniqueId id;
+    if (g_nccl.get_unique_id(&id) != 0) return SBV_ERR_NCCL;
+    memcpy(id128, id.internal, 128);
+    return SBV_OK;
+}
+
+// Adds one CHANNEL (an NCCL communicator over all ranks) and returns its index (>= 0) — call it once per concurrent
+// caller thread, with a fresh id each time, in the same order on every rank.
+int sbv_comm_init_rank(sbv_engine *e, const uint8_t *id128, int nranks, int rank) {
+    if (!e || !id128 || nranks < 1 || rank < 0 || rank >= nranks || e->devs.size() != 1)
+        return fail(e, SBV_ERR_ARG, "sbv_comm_init_rank: bad argument (needs a single-device engine)");
+    if (!e->rank_comms.empty() && (e->nranks != nranks || e->rank != rank)) return fail(e, SBV_ERR_ARG, "sbv_comm_init_rank: rank / nranks changed");
+    if (int rc = nccl_load(e)) return rc;
+    Dev &d = e->devs[0];
+    CU(e, cudaSetDevice(d.ordinal));
+    NcclUniqueId id;
+    memcpy(id.internal, id128, 128);
+    void *comm = nullptr;
+    NC(e, g_nccl.comm_init_rank(&comm, nranks, id, rank));
+    std::lock_guard<std::mutex> lk(e->mu);
+    e->rank_comms.push_back(comm);
+    e->rank = rank;
+    e->nranks = nranks;
+    return (int)e->rank_comms.size() - 1;
+}
+
+int sbv_comm_ranks(const sbv_engine *e) { return e ? e->nranks : 0; }
+
+// Packs n verdict bytes on the device into a bitmask and all-gathers the masks of all ranks over `channel`:
+// d_mask_all[rank * words_per_rank + w], words_per_rank = ceil(n / 32) (every rank passes the same n).
+// Enqueued on cuda_stream behind whatever produced d_ok; not synchronised.
+int sbv_gather_verdicts_device(sbv_engine *e, int channel, const uint8_t *d_ok, size_t n, uint32_t *d_mask_all, void *cuda_stream) {
+    if (!e || e->devs.size() != 1 || !d_ok || !d_mask_all || n == 0 || n > 0x7fffffffu) return fail(e, SBV_ERR_ARG, "sbv_gather_verdicts_device: bad argument");
+    Dev &d = e->devs[0];
+    CU(e, cudaSetDevice(d.ordinal));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t wp = (n + 31) / 32;
+    uint32_t *mine = d_mask_all + wp * (size_t)e->rank;
+    k_pack_bits<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>((uint32_t)n, d_ok, mine);
+    e->launches += 1;
+    CU(e, cudaGetLastError());
+    if (e->nranks > 1) {
+        if (channel < 0 || channel >= (int)e->rank_comms.size()) return fail(e, SBV_ERR_NCCL, "no such channel: call sbv_comm_init_rank first");
+        NC(e, g_nccl.all_gather(mine, d_mask_all, wp, NCCL_UINT32, e->rank_comms[channel], st));
     }
     return SBV_OK;
+}
+
+// All-gather of `words` 32-bit words per rank (already on the device): d_all[rank * words + w].  The sender's words
+// must sit at d_all + rank * words (in place).  Used for the per-instance `reached` bitmask of the quorum path.
+int sbv_gather_words_device(sbv_engine *e, int channel, uint32_t *d_all, size_t words, void *cuda_stream) {
+    if (!e || e->devs.size() != 1 || !d_all || words == 0) return fail(e, SBV_ERR_ARG, "sbv_gather_words_device: bad argument");
+    if (e->nranks == 1) return SBV_OK;
+    if (channel < 0 || channel >= (int)e->rank_comms.size()) return fail(e, SBV_ERR_NCCL, "no such channel: call sbv_comm_init_rank first");
+    CU(e, cudaSetDevice(e->devs[0].ordinal));
+    NC(e, g_nccl.all_gather(d_all + words * (size_t)e->rank, d_all, words, NCCL_UINT32, e->rank_comms[channel], (cudaStream_t)cuda_stream));
+    return SBV_OK;
+}
+
+// Host-buffer form for a rank: this rank's n items are verified, its verdict bytes go to ok (n bytes) and the packed
+// masks of ALL ranks to mask_all (nranks * ceil(n/32) words).  Every rank calls it with the same n, and the calls of
+// one channel are issued in the same order on every rank.
+int sbv_verify_batch_ranked(sbv_engine *e, int channel, uint8_t curve, size_t n, const uint8_t *r, const uint8_t *s, const uint8_t *qx,
+                            const uint8_t *qy, const uint8_t *digest, uint8_t digest_len, uint8_t *ok, uint32_t *mask_all) {
+    if (!e || curve > SBV_P384 || digest_len == 0 || (digest_len & 3) || digest_len > 64 || e->devs.size() != 1)
+        return fail(e, SBV_ERR_ARG, "sbv_verify_batch_ranked: bad argument");
+    if (n == 0 || n > 0x7fffffffu) return fail(e, SBV_ERR_ARG, "n must be in [1, 2^31)");
+    if (!r || !s || !qx || !qy || !digest || !ok || !mask_all) return fail(e, SBV_ERR_ARG, "null buffer");
+    LaneGuard guard(e);
+    const int lane = guard.lane;
+    Dev &d = e->devs[0];
+    Dev::Lane &ln = d.lanes[lane];
+    int rc = stage_and_verify(e, d, lane, curve, 0, n, r, s, qx, qy, digest, digest_len);
+    if (rc) return rc;
+    const size_t wp = (n + 31) / 32;
+    if ((rc = sbv_lane_ensure_aux(e, ln, wp * (size_t)e->nranks * 4))) return rc;
+    CU(e, cudaMemcpyAsync(ok, ln.d_ok, n, cudaMemcpyDeviceToHost, ln.stream));
+    if ((rc = sbv_gather_verdicts_device(e, channel, ln.d_ok, n, (uint32_t *)ln.d_aux, ln.stream))) return rc;
+    CU(e, cudaMemcpyAsync(mask_all, ln.d_aux, wp * (size_t)e->nranks * 4, cudaMemcpyDeviceToHost, ln.stream));
+    return sync_lane(e, lane);
 }
 
 double sbv_probe_mad_rate(sbv_engine *e) {
@@ -543,7 +563,7 @@ double sbv_probe_mad_rate(sbv_engine *e) {
     std::lock_guard<std::mutex> lk(e->mu);
     Dev &d = e->devs[0];
     if (cudaSetDevice(d.ordinal) != cudaSuccess) return 0.0;
-    if (ensure_scratch(e, d, 4096)) return 0.0;
+    if (sbv_ensure_scratch(e, d, 4096)) return 0.0;
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, d.ordinal);
     const uint32_t iters = 4096;
@@ -573,7 +593,7 @@ double sbv_probe_mad_rate(sbv_engine *e) {
 
 #include "engine_more.inc"
 
-// ---- profiling hooks (bench.py's roofline leg): CUDA-event timing of the prep / verify kernels ----
+// ---- profiling hooks (bench.py's roofline leg): CUDA-event timing inside every verify launch ----
 extern "C" {
 
 int sbv_profile_enable(sbv_engine *e, int on) {
@@ -584,26 +604,28 @@ int sbv_profile_enable(sbv_engine *e, int on) {
     return SBV_OK;
 }
 
-// Sums the recorded intervals (all devices), then resets.  Caller must have synchronised the streams.
-int sbv_profile_read(sbv_engine *e, double *prep_ms, double *verify_ms, uint64_t *n_pairs) {
+// Sums the recorded intervals (all devices), then resets: prep_ms = start .. end of k_prep (includes the key grouping),
+// verify_ms = the dominant verify kernel alone (k_verify_kt when keys were grouped, k_verify_coz otherwise).
+// The caller must have synchronised the streams it used.
+int sbv_profile_read(sbv_engine *e, double *prep_ms, double *verify_ms, uint64_t *n_launches) {
     if (!e) return SBV_ERR_ARG;
     std::lock_guard<std::mutex> lk(e->mu);
     double p = 0, v = 0;
     uint64_t cnt = 0;
     for (Dev &d : e->devs) {
         CU(e, cudaSetDevice(d.ordinal));
-        for (size_t i = 0; i + 2 < d.prof_used + 0 && i + 2 < d.prof_events.size(); i += 3) {
+        for (size_t i = 0; i + 3 < d.prof_used && i + 3 < d.prof_events.size(); i += 4) {
             float a = 0, b = 0;
-            CU(e, cudaEventSynchronize(d.prof_events[i + 2]));
+            CU(e, cudaEventSynchronize(d.prof_events[i + 3]));
             CU(e, cudaEventElapsedTime(&a, d.prof_events[i], d.prof_events[i + 1]));
-            CU(e, cudaEventElapsedTime(&b, d.prof_events[i + 1], d.prof_events[i + 2]));
+            CU(e, cudaEventElapsedTime(&b, d.prof_events[i + 2], d.prof_events[i + 3]));
             p += a; v += b; cnt++;
         }
         d.prof_used = 0;
     }
     if (prep_ms) *prep_ms = p;
     if (verify_ms) *verify_ms = v;
-    if (n_pairs) *n_pairs = cnt;
+    if (n_launches) *n_launches = cnt;
     return SBV_OK;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdint>
@@ -11,27 +12,42 @@
 #include <vector>
 
 #include "../../include/sbv.h"
+#include "ops.h"
+
+constexpr int SBV_LANES = 3;    // concurrent host-buffer calls per engine
+constexpr int SBV_SCRATCH = 4;  // verify launches in flight per device
 
 struct Dev {
     int ordinal = 0;
     cudaStream_t stream = nullptr;
     uint32_t *gtab[2] = {nullptr, nullptr};
-    // per-batch workspace (device)
-    size_t cap = 0;
-    uint8_t *d_r = nullptr, *d_s = nullptr, *d_qx = nullptr, *d_qy = nullptr, *d_dig = nullptr, *d_ok = nullptr;
-    // k_prep -> k_verify scratch, double-buffered so that launches on different streams may overlap:
-    // a launch takes the next set and first waits for the event of that set's previous user.
+    // Per-launch workspace of the verify pipeline.  A launch takes the next set and first waits for the event of
+    // that set's previous user, so launches on different streams overlap without sharing mutable state.
     struct Scratch {
-        uint16_t *gidx = nullptr;
-        int8_t *digits = nullptr;
-        uint8_t *flags = nullptr;
-        uint32_t *tscr = nullptr;  // k_verify_coz per-signature scratch: 12N words, word-major
-        cudaEvent_t done = nullptr;
+        size_t cap = 0;   // items
+        size_t kcap = 0;  // keys with a table per launch
+        uint32_t *uw = nullptr;     // k_prep output: u1, u2 word-major [2N][cap]
+        uint8_t *flags = nullptr;   // r, s range verdicts
+        uint32_t *tscr = nullptr;   // k_verify_coz per-signature scratch: 12N words, word-major
+        // key grouping
+        uint32_t hsize = 0;
+        uint32_t *htab = nullptr, *rep = nullptr, *keylist = nullptr, *klist = nullptr, *glist = nullptr;
+        uint32_t *zeroed = nullptr;  // one memset: counters[4] then kcnt[cap]
+        int32_t *keyid = nullptr, *item_kid = nullptr;
+        // per-key tables of the launch
+        uint32_t *bases = nullptr, *hs = nullptr, *ztop = nullptr, *pref = nullptr, *ktab = nullptr;
+        uint8_t *keyflags = nullptr;
+        cudaStream_t s_tab = nullptr, s_gen = nullptr;  // table construction / generic kernel run beside the main stream
+        cudaEvent_t done = nullptr, ev_group = nullptr, ev_prep = nullptr, ev_tab = nullptr, ev_gen = nullptr;
         bool used = false;
-    } ws[4];
+        struct Caps {  // bytes allocated per buffer
+            size_t uw = 0, flags = 0, tscr = 0, htab = 0, rep = 0, keylist = 0, klist = 0, glist = 0, zeroed = 0, keyid = 0, item_kid = 0, bases = 0,
+                   hs = 0, ztop = 0, pref = 0, ktab = 0, keyflags = 0;
+        } caps;
+    } ws[SBV_SCRATCH];
     unsigned ws_next = 0;
-    // per-call lanes of the host-buffer entry points: own stream, input/verdict buffers and pinned staging, so
-    // two host threads can have a call in flight each (H2D / kernels / D2H of one overlap the other's)
+    // Per-call lanes of the host-buffer entry points: own stream, input/verdict buffers and pinned staging, so that
+    // SBV_LANES host threads can have a call in flight each (H2D / kernels / D2H of one overlap the others').
     struct Lane {
         cudaStream_t stream = nullptr;
         size_t cap = 0;
@@ -43,43 +59,46 @@ struct Dev {
         size_t msg_cap = 0, off_cap = 0;
         uint8_t *h_pin = nullptr;
         size_t h_pin_cap = 0;
-    } lanes[2];
-    // message workspace
-    size_t msg_cap = 0, off_cap = 0;
-    uint8_t *d_msgs = nullptr;
-    uint64_t *d_off = nullptr;
-    uint32_t *d_perm = nullptr;
-    // pinned staging
-    uint8_t *h_pin = nullptr;
-    size_t h_pin_cap = 0;
-    // generic scratch (quorum, bitmask)
+        // small device scratch (quorum inputs / counts, packed verdict masks) and its pinned mirror
+        uint8_t *d_aux = nullptr, *h_aux = nullptr;
+        size_t aux_cap = 0;
+        // second stream of the call (mixed-curve batches run their two pipelines side by side)
+        cudaStream_t stream2 = nullptr;
+        cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    } lanes[SBV_LANES];
+    // generic scratch of the entry points that serialise on the engine lock
     uint8_t *d_scratch = nullptr;
     size_t scratch_cap = 0;
-    // registered keys (sbv_set_keys): per-curve comb tables, validity flags, slot -> table index
+    // registered keys (sbv_set_keys): per-curve tables (8-bit signed windows), validity flags, slot -> table index
     uint32_t *ktab[2] = {nullptr, nullptr};
     uint8_t *keyflags[2] = {nullptr, nullptr};
     int32_t *slot2local[2] = {nullptr, nullptr};
     uint32_t n_slots = 0, n_local[2] = {0, 0};
-    // profiling: event pairs around the prep / verify kernels (only when enabled)
-    std::vector<cudaEvent_t> prof_events;  // triples: before prep, between, after verify
+    // profiling: event quadruples per verify launch (start, after prep, before / after the dominant kernel)
+    std::vector<cudaEvent_t> prof_events;
     size_t prof_used = 0;
 };
 
 struct sbv_engine {
     std::vector<Dev> devs;
-    std::mutex mu;
+    std::mutex mu;       // kernel enqueue + workspace growth
+    std::mutex err_mu;   // last-error string
     std::condition_variable lane_cv;
-    bool lane_busy[2] = {false, false};
+    bool lane_busy[SBV_LANES] = {};
     std::string err;
-    uint64_t launches = 0;
-    int keyed_warp_limit = 2048;  // registered-key batches up to this size use one warp per signature (SBV_KEYED_WARP_LIMIT)
-    int p384_variant = 1;  // 1 = co-Z 4-bit window, 0 = 3-bit Jacobian window (SBV_P384_VARIANT)
-    int p256_variant = 1;  // 1 = co-Z 4-bit window (default), 2 = co-Z with one lockstep 448-thread block per SM, 0 = 3-bit Jacobian window
+    std::atomic<uint64_t> launches{0};
+    int keyed_warp_limit = 2048;   // registered-key batches up to this size use one warp per signature (SBV_KEYED_WARP_LIMIT)
+    int group_threshold = 16;      // a key gets a table when it occurs at least this often in a batch (SBV_GROUP_THRESHOLD; 0 = never)
+    int group_max_keys = 8192;     // table slots per launch (SBV_GROUP_MAX_KEYS)
+    uint32_t hash_seed = 0x9e3779b9u;
     bool profiling = false;
-    // NCCL (multi-device only; loaded lazily with dlopen so single-device users never touch it)
+    // NCCL (loaded lazily with dlopen so single-device, single-rank users never touch it)
     void *nccl_lib = nullptr;
-    std::vector<void *> nccl_comms;
-    std::vector<uint32_t> gather_words;  // host copy of the gathered verdict bitmask
+    std::vector<void *> nccl_comms;  // one per device of a multi-device engine
+    // one-process-per-GPU deployments: this engine is rank `rank` of `nranks`.  One communicator per CHANNEL: the
+    // collectives of a channel must be issued in the same order on every rank, so concurrent host threads take one each.
+    std::vector<void *> rank_comms;
+    int rank = 0, nranks = 1;
     // key registry
     uint64_t verification_seq = 0;
     std::vector<uint64_t> key_ids;
@@ -93,7 +112,10 @@ inline int sbv_fail(sbv_engine *e, int code, const char *fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
-    if (e) e->err = buf;
+    if (e) {
+        std::lock_guard<std::mutex> lk(e->err_mu);
+        e->err = buf;
+    }
     return code;
 }
 #define fail sbv_fail
@@ -106,33 +128,46 @@ inline int sbv_fail(sbv_engine *e, int code, const char *fmt, ...) {
                             __FILE__, __LINE__);                                                      \
     } while (0)
 
-// per-(curve, window, block) kernel launchers — one translation unit each (inst_*.cu)
-int sbv_launch_p256_w3_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
-                           const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
-int sbv_launch_p256_coz_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
-                            const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
-int sbv_launch_p256_coz_b448(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
-                             const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
-int sbv_launch_p384_coz_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
-                            const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
-int sbv_launch_p384_w3_b64(sbv_engine *e, Dev &d, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
-                            const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
-int sbv_init_gtables(sbv_engine *e, Dev &d);  // gtable.cu
-int sbv_keys_build(sbv_engine *e, Dev &d);    // keyed.cu: (re)builds the per-key comb tables from the registry
-void sbv_keys_free(Dev &d);
+// ---- pipeline.cu: the verify pipelines (device pointers in, verdict bytes out; enqueue only, no sync) ----
+// keys-per-item: k_prep, key grouping, per-key tables for repeated keys, fixed-base kernel + generic kernel for the rest
+int sbv_launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
+                      const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
+// registered keys (sbv_set_keys)
 int sbv_launch_keyed(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint32_t *d_slot, const uint8_t *d_r, const uint8_t *d_s,
                      const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
-int sbv_ensure_workspace(sbv_engine *e, Dev &d, size_t n);
-int sbv_ensure_pinned(sbv_engine *e, Dev &d, size_t bytes);
-int sbv_h2d(sbv_engine *e, Dev &d, void *dst, const void *src, size_t bytes, size_t &stage_off, cudaStream_t st);
+int sbv_init_gtables(sbv_engine *e, Dev &d);
+int sbv_keys_build(sbv_engine *e, Dev &d);  // (re)builds the per-key tables of the registry
+void sbv_keys_free(Dev &d);
+void sbv_scratch_free(Dev &d);
+
+// ---- engine.cu helpers shared with the other translation units ----
 int sbv_lane_acquire(sbv_engine *e);            // blocks until a lane index is free; returns it
 void sbv_lane_release(sbv_engine *e, int lane);
 int sbv_lane_ensure(sbv_engine *e, Dev &d, Dev::Lane &ln, size_t n, size_t pinned_bytes);
 int sbv_lane_ensure_msgs(sbv_engine *e, Dev::Lane &ln, size_t bytes, size_t n_off);
+int sbv_lane_ensure_aux(sbv_engine *e, Dev::Lane &ln, size_t bytes);
 // d_perm: n + 3072 words of scratch (may be null: no length sort)
 int sbv_launch_sha256(sbv_engine *e, size_t n, const uint8_t *d_msgs, const uint64_t *d_off, uint64_t base, uint8_t *d_digest, uint32_t *d_perm,
                       cudaStream_t st);
 int sbv_lane_h2d(sbv_engine *e, Dev::Lane &ln, void *dst, const void *src, size_t bytes, size_t &stage_off);
 int sbv_ensure_scratch(sbv_engine *e, Dev &d, size_t bytes);
-// takes the next scratch set of device d for a launch on stream st (waits for its previous user)
-int sbv_take_scratch(sbv_engine *e, Dev &d, cudaStream_t st, Dev::Scratch **out);
+
+// A host-buffer call owns one lane on every device for its duration.  On every exit path — faults included — the
+// lane's streams are drained before the lane is handed to the next caller, so no copy into the caller's buffers or out
+// of the lane's staging area is still in flight when the call returns (cgo contract of sbv.h).
+struct LaneGuard {
+    sbv_engine *e;
+    int lane;
+    explicit LaneGuard(sbv_engine *eng) : e(eng), lane(sbv_lane_acquire(eng)) {}
+    ~LaneGuard() {
+        for (Dev &d : e->devs) {
+            if (!d.lanes[lane].stream) continue;
+            cudaSetDevice(d.ordinal);
+            if (d.lanes[lane].stream2) cudaStreamSynchronize(d.lanes[lane].stream2);
+            cudaStreamSynchronize(d.lanes[lane].stream);
+        }
+        sbv_lane_release(e, lane);
+    }
+    LaneGuard(const LaneGuard &) = delete;
+    LaneGuard &operator=(const LaneGuard &) = delete;
+};

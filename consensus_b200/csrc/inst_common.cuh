@@ -1,0 +1,84 @@
+// inst_common.cuh — launcher templates behind ops.h.  Each inst_*.cu instantiates one group for one curve.
+#pragma once
+#include "keygroup.cuh"
+#include "ops.h"
+#include <cstdlib>
+
+namespace sbv {
+
+template <class C> struct Cfg;
+template <> struct Cfg<P256> { static constexpr int COZ_MINB = 7, KT_MINB = 7; };
+template <> struct Cfg<P384> { static constexpr int COZ_MINB = 4, KT_MINB = 4; };
+
+template <class C>
+cudaError_t op_gtable_init(uint32_t *gtab, cudaStream_t st) {
+    const size_t entries = (size_t)C::GWINS << C::GW;
+    k_gtable_init<C><<<(unsigned)((entries + 127) / 128), 128, 0, st>>>(gtab);
+    return cudaGetLastError();
+}
+
+template <class C>
+cudaError_t op_prep(uint32_t n, const uint8_t *r, const uint8_t *s, const uint8_t *dig, uint32_t dlen, uint32_t *uw, uint8_t *flags,
+                    cudaStream_t st) {
+    return launch_prep<C, 8>(n, r, s, dig, dlen, uw, flags, st);
+}
+
+template <class C>
+cudaError_t op_group(uint32_t n, const uint8_t *qx, const uint8_t *qy, uint32_t seed, uint32_t hmask, uint32_t *htab, uint32_t *rep,
+                     uint32_t *kcnt, uint32_t threshold, uint32_t max_keys, int32_t *keyid, uint32_t *keylist, int32_t *item_kid,
+                     uint32_t *klist, uint32_t *glist, uint32_t *counters, cudaStream_t st) {
+    const unsigned blocks = (n + 255) / 256;
+    k_kg_insert<C><<<blocks, 256, 0, st>>>(n, qx, qy, seed, hmask, htab, rep, kcnt);
+    k_kg_assign<<<blocks, 256, 0, st>>>(n, rep, kcnt, threshold, max_keys, keyid, keylist, counters);
+    k_kg_route<<<blocks, 256, 0, st>>>(n, rep, keyid, item_kid, klist, glist, counters);
+    return cudaGetLastError();
+}
+
+template <class C>
+cudaError_t op_coz(uint32_t n, const uint8_t *qx, const uint8_t *qy, const uint8_t *r, const uint32_t *uw, const uint8_t *flags,
+                   const uint32_t *gtab, uint32_t *tscr, uint8_t *ok, const uint32_t *list, const uint32_t *count, cudaStream_t st) {
+    constexpr int BLOCK = 64;
+    const size_t smem = (size_t)7 * 2 * C::N * 4 * BLOCK;  // < 48 KB for both curves: no opt-in attribute needed
+    k_verify_coz<C, BLOCK, Cfg<C>::COZ_MINB><<<(n + BLOCK - 1) / BLOCK, BLOCK, smem, st>>>(
+        n, qx, qy, r, uw, flags, reinterpret_cast<const uint4 *>(gtab), tscr, ok, list, count);
+    return cudaGetLastError();
+}
+
+template <class C, int W>
+cudaError_t op_kt_build(const uint32_t *nkeys_ptr, uint32_t cap, const uint32_t *keylist, const uint8_t *qx, const uint8_t *qy,
+                        uint32_t *bases, uint32_t *hs, uint32_t *ztop, uint32_t *pref, uint32_t *ktab, uint8_t *keyflags, cudaStream_t st) {
+    using KT = KeyTab<32 * C::N, W>;
+    const unsigned kb = (cap + 63) / 64;
+    const unsigned wb = (unsigned)(((size_t)cap * KT::NWIN + 63) / 64);
+    k_kt_bases<C, W><<<kb, 64, 0, st>>>(nkeys_ptr, cap, keylist, qx, qy, bases, keyflags);
+    k_kt_fill<C, W><<<wb, 64, 0, st>>>(nkeys_ptr, cap, bases, keyflags, hs, ztop, ktab);
+    k_kt_inv<C, W><<<kb, 64, 0, st>>>(nkeys_ptr, cap, keyflags, ztop, pref);
+    k_kt_final<C, W><<<wb, 64, 0, st>>>(nkeys_ptr, cap, bases, keyflags, hs, ztop, ktab);
+    return cudaGetLastError();
+}
+
+template <class C, int W>
+cudaError_t op_kt_verify(int reg, int warp, uint32_t n, const uint32_t *slot, const int32_t *kidmap, uint32_t n_slots,
+                         const uint8_t *keyflags, const uint8_t *r, const uint32_t *uw, const uint8_t *flags, const uint32_t *gtab,
+                         const uint32_t *ktab, uint8_t *ok, const uint32_t *list, const uint32_t *count, cudaStream_t st) {
+    constexpr int BLOCK = 64, MINB = Cfg<C>::KT_MINB;
+    static const bool relaxed = getenv("SBV_KT_RELAXED") != nullptr;  // A/B: one block fewer per SM, no register spills
+    const uint4 *g4 = reinterpret_cast<const uint4 *>(gtab), *k4 = reinterpret_cast<const uint4 *>(ktab);
+    if (warp)
+        k_verify_kt_warp<C, W><<<(unsigned)(((size_t)n * 32 + 127) / 128), 128, 0, st>>>(n, slot, kidmap, n_slots, keyflags, r, uw, flags, g4, k4, ok);
+    else if (relaxed && !reg)
+        k_verify_kt<C, W, BLOCK, MINB - 1, false><<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(n, slot, kidmap, n_slots, keyflags, r, uw, flags, g4, k4, ok, list, count);
+    else if (reg)
+        k_verify_kt<C, W, BLOCK, MINB, true><<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(n, slot, kidmap, n_slots, keyflags, r, uw, flags, g4, k4, ok, list, count);
+    else
+        k_verify_kt<C, W, BLOCK, MINB, false><<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(n, slot, kidmap, n_slots, keyflags, r, uw, flags, g4, k4, ok, list, count);
+    return cudaGetLastError();
+}
+
+template <class C, int W>
+constexpr KtGeom kt_geom() {
+    using KS = KtSizes<C, W>;
+    return KtGeom{W, KS::KT::NWIN, KS::KT::ENT, KS::bases_words(1), KS::hs_words(1), KS::ztop_words(1), KS::ktab_words(1)};
+}
+
+}  // namespace sbv

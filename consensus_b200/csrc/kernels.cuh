@@ -3,17 +3,17 @@
 //   k_gtable_init        one-time: affine fixed-base comb table  T[i][b] = b * 2^(GW*i) * G  (Montgomery form;
 //                        GW = 16 for P-256: 64 MiB, L2-resident; GW = 8 for P-384)
 //   k_prep               per batch: range checks, batched inversion of s mod n (Montgomery's trick over S items
-//                        per thread, one binary-extended-GCD inversion per thread), u1 = e/s, u2 = r/s, comb
-//                        digits of u1 and Booth digits (or comb bytes) of u2 written window-major so the verify
-//                        kernels read them coalesced
-//   k_verify_coz         keys-per-item path, ONE SIGNATURE PER THREAD: on-curve check, 4-bit signed window over a
-//                        common-Z table of Q (shared memory, bank = lane, + coalesced global scratch), 256
-//                        doublings interleaved with 65 additions, 16 comb additions for u1*G with the next gather
-//                        in flight, final X == r*Z^2 comparison (no inversion)
-//   k_verify             the same with a 3-bit Jacobian window table (A/B variant)
-//   k_keytab_init        registered keys: per-key affine comb table K[k][i][b] = b * 2^(8i) * Q_k
-//   k_verify_keyed       registered-key path, one signature per thread: 32 + 16 comb additions, no doublings
-//   k_verify_keyed_warp  registered-key path, ONE SIGNATURE PER WARP (small batches: lanes add their table points,
+//                        per thread, one binary-extended-GCD inversion per thread), u1 = e/s, u2 = r/s written
+//                        word-major ([2N][n] words) so that every consumer reads them coalesced and cuts its own
+//                        digits (comb digits of u1, Booth digits of u2 for whatever window it uses)
+//   k_verify_coz         keys-per-item path for keys that occur ONCE (or too rarely) in a batch, one signature per
+//                        thread: on-curve check, 4-bit signed window over a common-Z table of Q (shared memory,
+//                        bank = lane, + coalesced global scratch), 256 doublings interleaved with 65 additions, 16
+//                        comb additions for u1*G with the next gather in flight, final X == r*Z^2 comparison
+//   k_verify_kt          FIXED-BASE path for keys that have a per-key table (keygroup.cuh: built on the fly for keys
+//                        that repeat inside a batch, or once per registration for sbv_set_keys): no doublings,
+//                        NWIN(W) signed-window additions for u2*Q + the comb additions for u1*G
+//   k_verify_kt_warp     the same, ONE SIGNATURE PER WARP (small batches: lanes add their table points,
 //                        shuffle-tree reduction)
 //
 // Reference boundary: api.Verifier.VerifyConsenterSig / VerifySignature / VerifyRequest
@@ -94,13 +94,40 @@ SBV_DEV void load_digest(uint32_t (&e)[C::N], const uint8_t *d, uint32_t dlen) {
     }
 }
 
-template <class C, int W, int S>
+// ---- scalar digits, cut by the consumers from the word-major scalars uw[2N][n] (u1 words, then u2 words) ----
+// comb digit `win` of u1 (GW bits, little-endian); GW divides 32
+template <class C>
+SBV_DEV uint32_t comb_digit_u1(const uint32_t *__restrict__ uw, uint32_t n, uint32_t idx, int win) {
+    const int pos = win * C::GW;
+    return (__ldg(uw + (size_t)(pos >> 5) * n + idx) >> (pos & 31)) & ((1u << C::GW) - 1u);
+}
+// Booth digit `win` of u2 for a W-bit signed window: looks at bits [W*win - 1, W*win + W - 1] (bit -1 and the bits
+// above 32N are zero) and returns d in [-2^(W-1), 2^(W-1)]; sum d_i 2^(W i) = u2.
+template <class C, int W>
+SBV_DEV int booth_digit_u2(const uint32_t *__restrict__ uw, uint32_t n, uint32_t idx, int win) {
+    constexpr int N = C::N;
+    const uint32_t *u2 = uw + (size_t)N * n + idx;
+    const int pos = W * win - 1;
+    uint32_t b;
+    if (pos < 0) {
+        b = (__ldg(u2) << 1) & ((2u << W) - 1);
+    } else {
+        const int wd = pos >> 5, sh = pos & 31;
+        const uint32_t lo = wd < N ? __ldg(u2 + (size_t)wd * n) : 0u;
+        const uint32_t hi = wd + 1 < N ? __ldg(u2 + (size_t)(wd + 1) * n) : 0u;
+        b = __funnelshift_r(lo, hi, sh) & ((2u << W) - 1);
+    }
+    const uint32_t sign = b >> W;
+    uint32_t d = sign ? (((2u << W) - 1) - b) : b;
+    d = (d + 1) >> 1;
+    return sign ? -(int)d : (int)d;
+}
+
+template <class C, int S>
 __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restrict__ r_be, const uint8_t *__restrict__ s_be,
                                               const uint8_t *__restrict__ dig_be, uint32_t dlen,
-                                              uint16_t *__restrict__ gidx, int8_t *__restrict__ digits,
-                                              uint8_t *__restrict__ flags) {
+                                              uint32_t *__restrict__ uw, uint8_t *__restrict__ flags) {
     constexpr int N = C::N;
-    constexpr int NWIN = W == 0 ? C::BYTES : Windows<32 * N, (W == 0 ? 1 : W)>::COUNT;
     const uint32_t T = gridDim.x * blockDim.x;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t sm[S][N];    // Montgomery form of s (or 1 when out of range)
@@ -151,152 +178,35 @@ __global__ void __launch_bounds__(128) k_prep(uint32_t n, const uint8_t *__restr
             mp_copy<N>(w, inv);
         }
         // w = s^-1 in Montgomery form; u = x * w (plain) for x < 2^(32N)
-        uint32_t e[N], r[N], u1[N], u2[N + 1];
+        uint32_t e[N], r[N], u1[N], u2[N];
         load_digest<C>(e, dig_be + (size_t)idx * dlen, dlen);
         load_be<N>(r, r_be + (size_t)idx * C::BYTES);
         C::nmul(u1, e, w);
-        {
-            uint32_t tmp[N];
-            C::nmul(tmp, r, w);
+        C::nmul(u2, r, w);
 #pragma unroll
-            for (int i = 0; i < N; i++) u2[i] = tmp[i];
-            u2[N] = 0;
-        }
-        // comb digits of u1 (GW bits each, little-endian)
-#pragma unroll
-        for (int i = 0; i < C::GWINS; i++) gidx[(size_t)i * n + idx] = (uint16_t)((u1[(i * C::GW) >> 5] >> ((i * C::GW) & 31)) & ((1u << C::GW) - 1));
-        if (W == 0) {  // registered-key path: u2 is consumed by a second comb, byte-wise
-#pragma unroll
-            for (int i = 0; i < C::BYTES; i++) digits[(size_t)i * n + idx] = (int8_t)(uint8_t)(u2[i >> 2] >> (8 * (i & 3)));
-            continue;
-        }
-        // Booth digits of u2: window i looks at bits [W*i-1, W*i+W-1]
-        for (int i = 0; i < NWIN; i++) {
-            constexpr int WW = W == 0 ? 1 : W;
-            int pos = WW * i - 1;
-            uint32_t b;
-            if (pos < 0) {
-                b = (u2[0] << 1) & ((2u << WW) - 1);
-            } else {
-                int wd = pos >> 5, sh = pos & 31;
-                uint32_t lo = wd <= N ? u2[wd] : 0u, hi = wd + 1 <= N ? u2[wd + 1] : 0u;
-                uint64_t v = ((uint64_t)hi << 32) | lo;
-                b = (uint32_t)(v >> sh) & ((2u << WW) - 1);
-            }
-            uint32_t sign = b >> WW;
-            uint32_t d = sign ? (((2u << WW) - 1) - b) : b;
-            d = (d + 1) >> 1;
-            digits[(size_t)i * n + idx] = (int8_t)(sign ? -(int)d : (int)d);
+        for (int i = 0; i < N; i++) {
+            uw[(size_t)i * n + idx] = u1[i];
+            uw[(size_t)(N + i) * n + idx] = u2[i];
         }
     }
 }
 
+#ifdef __CUDACC__
 // host-side launcher of k_prep
-template <class C, int W, int S>
-inline cudaError_t launch_prep(uint32_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_dig, uint32_t dlen, uint16_t *gidx,
-                               int8_t *digits, uint8_t *flags, cudaStream_t st) {
+template <class C, int S>
+inline cudaError_t launch_prep(uint32_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_dig, uint32_t dlen, uint32_t *uw,
+                               uint8_t *flags, cudaStream_t st) {
     constexpr int PB = 128;
     const uint32_t pthreads = (n + S - 1) / S;
-    k_prep<C, W, S><<<(pthreads + PB - 1) / PB, PB, 0, st>>>(n, d_r, d_s, d_dig, dlen, gidx, digits, flags);
+    k_prep<C, S><<<(pthreads + PB - 1) / PB, PB, 0, st>>>(n, d_r, d_s, d_dig, dlen, uw, flags);
     return cudaGetLastError();
 }
+#endif
 
-// ------------------------------------------------------------------------------------------------
-template <class C, int W, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) k_verify(uint32_t n, const uint8_t *__restrict__ qx_be, const uint8_t *__restrict__ qy_be,
-                                                  const uint8_t *__restrict__ r_be, const uint16_t *__restrict__ gidx,
-                                                  const int8_t *__restrict__ digits, const uint8_t *__restrict__ flags,
-                                                  const uint4 *__restrict__ gtab, uint8_t *__restrict__ ok_out) {
+// accept iff R != inf and R.x mod n == r  <=>  X == r*Z^2 or (r + n < p and X == (r+n)*Z^2)
+template <class C>
+SBV_DEV bool final_check(const Jac<C> &acc, const uint8_t *__restrict__ r_be, uint32_t idx) {
     constexpr int N = C::N;
-    constexpr int NWIN = Windows<32 * N, W>::COUNT;
-    constexpr int TE = Windows<32 * N, W>::ENTRIES;
-    extern __shared__ uint32_t tab[];  // [(entry*3 + coord)*N + limb][BLOCK]
-    const uint32_t tid = threadIdx.x;
-    const uint32_t idx = blockIdx.x * BLOCK + tid;
-    if (idx >= n) return;  // the table is thread-private: no block-wide barrier anywhere
-#define TAB(e, c, w) tab[(((e) * 3 + (c)) * N + (w)) * BLOCK + tid]
-
-    uint32_t pmod[N], one[N];
-    C::get_p(pmod);
-    C::get_one(one);
-    bool good = flags[idx] != 0;
-    {
-        uint32_t x[N], y[N], rr[N];
-        load_be<N>(x, qx_be + (size_t)idx * C::BYTES);
-        load_be<N>(y, qy_be + (size_t)idx * C::BYTES);
-        good = good && mp_lt<N>(x, pmod) && mp_lt<N>(y, pmod);
-        C::get_rr_p(rr);
-        Jac<C> P;
-        C::fmul(P.X, x, rr);
-        C::fmul(P.Y, y, rr);
-        mp_copy<N>(P.Z, one);
-        // y^2 == x^3 - 3x + b
-        uint32_t lhs[N], rhs[N], t[N], b[N];
-        C::fsqr(lhs, P.Y);
-        C::fsqr(t, P.X);
-        C::fmul(rhs, t, P.X);
-        C::fsub(rhs, rhs, P.X);
-        C::fsub(rhs, rhs, P.X);
-        C::fsub(rhs, rhs, P.X);
-        C::get_b(b);
-        C::fadd(rhs, rhs, b);
-        good = good && mp_eq<N>(lhs, rhs);
-        // table: entry k-1 holds k*Q (Jacobian)
-        uint32_t qxm[N], qym[N];
-        mp_copy<N>(qxm, P.X);
-        mp_copy<N>(qym, P.Y);
-#pragma unroll 1
-        for (int k = 0; k < TE; k++) {
-            if (k == 1) pt_double<C>(P);
-            else if (k > 1) pt_add<C, true>(P, qxm, qym, one, false, false);
-#pragma unroll
-            for (int i = 0; i < N; i++) { TAB(k, 0, i) = P.X[i]; TAB(k, 1, i) = P.Y[i]; TAB(k, 2, i) = P.Z[i]; }
-        }
-    }
-    Jac<C> acc;
-    mp_copy<N>(acc.X, one);
-    mp_copy<N>(acc.Y, one);
-#pragma unroll
-    for (int i = 0; i < N; i++) acc.Z[i] = 0;
-
-#pragma unroll 1
-    for (int win = NWIN - 1; win >= 0; win--) {
-        if (win != NWIN - 1) {
-#pragma unroll 1
-            for (int k = 0; k < W; k++) pt_double<C>(acc);
-        }
-        {
-            int d = digits[(size_t)win * n + idx];
-            bool neg = d < 0, skip = d == 0;
-            int e = (neg ? -d : d) - 1;
-            e = skip ? 0 : e;
-            uint32_t x2[N], y2[N], z2[N];
-#pragma unroll
-            for (int i = 0; i < N; i++) { x2[i] = TAB(e, 0, i); y2[i] = TAB(e, 1, i); z2[i] = TAB(e, 2, i); }
-            pt_add<C, false>(acc, x2, y2, z2, neg, skip);
-        }
-    }
-    // u1*G from the fixed-base comb: GWINS complete points, added after the last doubling.  The next
-    // entry (a random 64 B gather from the L2-resident table) is in flight while the current one is added.
-    {
-        constexpr int EU4 = 2 * N / 4;
-        uint32_t gx[N], gy[N];
-        uint32_t gb = gidx[idx];
-        load_affine<C>(gx, gy, gtab + (size_t)gb * EU4);
-#pragma unroll 1
-        for (int win = 0; win < C::GWINS; win++) {
-            uint32_t ngx[N], ngy[N];
-            uint32_t ngb = 0;
-            if (win + 1 < C::GWINS) {
-                ngb = gidx[(size_t)(win + 1) * n + idx];
-                load_affine<C>(ngx, ngy, gtab + (((size_t)(win + 1) << C::GW) + ngb) * EU4);
-            }
-            pt_add<C, true>(acc, gx, gy, one, false, gb == 0);
-            if (win + 1 < C::GWINS) { mp_copy<N>(gx, ngx); mp_copy<N>(gy, ngy); gb = ngb; }
-        }
-    }
-#undef TAB
-    // accept iff R != inf and R.x mod n == r  <=>  X == r*Z^2 or (r + n < p and X == (r+n)*Z^2)
     bool match = false;
     if (!mp_is_zero<N>(acc.Z)) {
         uint32_t zz[N], r[N], rr[N], rm[N], lhs[N], pmn[N];
@@ -316,191 +226,86 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_verify(uint32_t n, const uint8_
             match = mp_eq<N>(lhs, acc.X);
         }
     }
-    ok_out[idx] = (good && match) ? 1 : 0;
+    return match;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Registered-key path (sbv_set_keys): per-key affine comb table K[k][i][b] = b * 2^(8i) * Q_k, so
-// u2*Q is fixed-base as well — no doublings and no per-signature table.
+// key (x, y big-endian) -> Montgomery form; false unless both coordinates < p and y^2 == x^3 - 3x + b
 template <class C>
-__global__ void k_keytab_init(uint32_t n_keys, const uint8_t *__restrict__ keys_be, uint32_t *__restrict__ tab,
-                              uint8_t *__restrict__ keyflags) {
+SBV_DEV bool load_key(uint32_t (&qxm)[C::N], uint32_t (&qym)[C::N], const uint8_t *__restrict__ qx_be, const uint8_t *__restrict__ qy_be, uint32_t idx) {
     constexpr int N = C::N;
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t per_key = (size_t)C::BYTES * 256;
-    if (t >= (size_t)n_keys * per_key) return;
-    const uint32_t key = (uint32_t)(t / per_key);
-    const int e = (int)(t % per_key), win = e >> 8, b = e & 255;
-    uint32_t *out = tab + t * 2 * N;
-    uint32_t x[N], y[N], pmod[N], rr[N];
-    load_be<N>(x, keys_be + (size_t)key * 2 * C::BYTES);
-    load_be<N>(y, keys_be + (size_t)key * 2 * C::BYTES + C::BYTES);
+    uint32_t x[N], y[N], rr[N], pmod[N];
     C::get_p(pmod);
-    C::get_rr_p(rr);
+    load_be<N>(x, qx_be + (size_t)idx * C::BYTES);
+    load_be<N>(y, qy_be + (size_t)idx * C::BYTES);
     bool good = mp_lt<N>(x, pmod) && mp_lt<N>(y, pmod);
-    Jac<C> base;
-    C::fmul(base.X, x, rr);
-    C::fmul(base.Y, y, rr);
-    C::get_one(base.Z);
-    {
-        uint32_t lhs[N], rhs[N], tt[N], bb[N];
-        C::fsqr(lhs, base.Y);
-        C::fsqr(tt, base.X);
-        C::fmul(rhs, tt, base.X);
-        C::fsub(rhs, rhs, base.X); C::fsub(rhs, rhs, base.X); C::fsub(rhs, rhs, base.X);
-        C::get_b(bb);
-        C::fadd(rhs, rhs, bb);
-        good = good && mp_eq<N>(lhs, rhs);
-    }
-    if (e == 0) keyflags[key] = good ? 1 : 0;
-    if (b == 0 || !good) {
-        for (int i = 0; i < 2 * N; i++) out[i] = 0;
-        return;
-    }
-    for (int i = 0; i < 8 * win; i++) pt_double<C>(base);
-    Jac<C> acc;
-    C::get_one(acc.X); C::get_one(acc.Y);
-#pragma unroll
-    for (int i = 0; i < N; i++) acc.Z[i] = 0;
-    for (int bit = 7; bit >= 0; bit--) {
-        pt_double<C>(acc);
-        pt_add<C, false>(acc, base.X, base.Y, base.Z, false, !((b >> bit) & 1));
-    }
-    uint32_t zi[N], zi2[N], zi3[N], ox[N], oy[N];
-    f_inv<C>(zi, acc.Z);
-    C::fsqr(zi2, zi);
-    C::fmul(zi3, zi2, zi);
-    C::fmul(ox, acc.X, zi2);
-    C::fmul(oy, acc.Y, zi3);
-    for (int i = 0; i < N; i++) { out[i] = ox[i]; out[N + i] = oy[i]; }
+    C::get_rr_p(rr);
+    C::fmul(qxm, x, rr);
+    C::fmul(qym, y, rr);
+    uint32_t lhs[N], rhs[N], t[N], b[N];
+    C::fsqr(lhs, qym);
+    C::fsqr(t, qxm);
+    C::fmul(rhs, t, qxm);
+    C::fsub(rhs, rhs, qxm); C::fsub(rhs, rhs, qxm); C::fsub(rhs, rhs, qxm);
+    C::get_b(b);
+    C::fadd(rhs, rhs, b);
+    return good && mp_eq<N>(lhs, rhs);
 }
 
-template <class C, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) k_verify_keyed(uint32_t n, const uint32_t *__restrict__ slot, const int32_t *__restrict__ slot2local,
-                                                        uint32_t n_slots, const uint8_t *__restrict__ keyflags,
-                                                        const uint8_t *__restrict__ r_be, const uint16_t *__restrict__ gidx,
-                                                        const uint8_t *__restrict__ qidx, const uint8_t *__restrict__ flags,
-                                                        const uint4 *__restrict__ gtab, const uint4 *__restrict__ ktab,
-                                                        uint8_t *__restrict__ ok_out) {
+// acc += u1*G from the fixed-base comb: GWINS complete points.  The next entry (a random gather from the
+// L2-resident table) is in flight while the current one is added.
+template <class C>
+SBV_DEV void add_u1G(Jac<C> &acc, const uint32_t *__restrict__ uw, uint32_t n, uint32_t idx, const uint4 *__restrict__ gtab) {
     constexpr int N = C::N;
-    constexpr int EU4 = 2 * N / 4;  // uint4 per table entry
-    const uint32_t idx = blockIdx.x * BLOCK + threadIdx.x;
-    if (idx >= n) return;
-    bool good = flags[idx] != 0;
-    const uint32_t sl = slot[idx];
-    int32_t local = sl < n_slots ? slot2local[sl] : -1;
-    good = good && local >= 0;
-    if (local < 0) local = 0;
-    good = good && keyflags[local] != 0;
-    const uint4 *kt = ktab + (size_t)local * C::BYTES * 256 * EU4;
+    constexpr int EU4 = 2 * N / 4;
     uint32_t one[N];
     C::get_one(one);
-    Jac<C> acc;
-    mp_copy<N>(acc.X, one);
-    mp_copy<N>(acc.Y, one);
-#pragma unroll
-    for (int i = 0; i < N; i++) acc.Z[i] = 0;
-    // software pipeline: the table entries of the next step are in flight while the current one is added
-    uint32_t kx[N], ky[N];
-    uint32_t kb = qidx[idx];
-    load_affine<C>(kx, ky, kt + (size_t)kb * EU4);
+    uint32_t gx[N], gy[N];
+    uint32_t gb = comb_digit_u1<C>(uw, n, idx, 0);
+    load_affine<C>(gx, gy, gtab + (size_t)gb * EU4);
 #pragma unroll 1
-    for (int win = 0; win < C::BYTES; win++) {  // u2 * Q_k : 8-bit comb of the registered key
-        uint32_t nkx[N], nky[N];
-        uint32_t nkb = 0;
-        if (win + 1 < C::BYTES) {
-            nkb = qidx[(size_t)(win + 1) * n + idx];
-            load_affine<C>(nkx, nky, kt + ((size_t)(win + 1) * 256 + nkb) * EU4);
+    for (int win = 0; win < C::GWINS; win++) {
+        uint32_t ngx[N], ngy[N];
+        uint32_t ngb = 0;
+        if (win + 1 < C::GWINS) {
+            ngb = comb_digit_u1<C>(uw, n, idx, win + 1);
+            load_affine<C>(ngx, ngy, gtab + (((size_t)(win + 1) << C::GW) + ngb) * EU4);
         }
-        pt_add<C, true>(acc, kx, ky, one, false, kb == 0);
-        if (win + 1 < C::BYTES) { mp_copy<N>(kx, nkx); mp_copy<N>(ky, nky); kb = nkb; }
+        pt_add<C, true>(acc, gx, gy, one, false, gb == 0);
+        if (win + 1 < C::GWINS) { mp_copy<N>(gx, ngx); mp_copy<N>(gy, ngy); gb = ngb; }
     }
-    {
-        uint32_t gx[N], gy[N];
-        uint32_t gb = gidx[idx];
-        load_affine<C>(gx, gy, gtab + (size_t)gb * EU4);
-#pragma unroll 1
-        for (int win = 0; win < C::GWINS; win++) {  // u1 * G : GW-bit comb
-            uint32_t ngx[N], ngy[N];
-            uint32_t ngb = 0;
-            if (win + 1 < C::GWINS) {
-                ngb = gidx[(size_t)(win + 1) * n + idx];
-                load_affine<C>(ngx, ngy, gtab + (((size_t)(win + 1) << C::GW) + ngb) * EU4);
-            }
-            pt_add<C, true>(acc, gx, gy, one, false, gb == 0);
-            if (win + 1 < C::GWINS) { mp_copy<N>(gx, ngx); mp_copy<N>(gy, ngy); gb = ngb; }
-        }
-    }
-    bool match = false;
-    if (!mp_is_zero<N>(acc.Z)) {
-        uint32_t zz[N], r[N], rr[N], rm[N], lhs[N], pmn[N];
-        C::fsqr(zz, acc.Z);
-        load_be<N>(r, r_be + (size_t)idx * C::BYTES);
-        C::get_rr_p(rr);
-        C::fmul(rm, r, rr);
-        C::fmul(lhs, rm, zz);
-        match = mp_eq<N>(lhs, acc.X);
-        C::get_p_minus_n(pmn);
-        if (!match && mp_lt<N>(r, pmn)) {
-            uint32_t r2[N], nmod[N];
-            C::get_n(nmod);
-            mp_add<N>(r2, r, nmod);
-            C::fmul(rm, r2, rr);
-            C::fmul(lhs, rm, zz);
-            match = mp_eq<N>(lhs, acc.X);
-        }
-    }
-    ok_out[idx] = (good && match) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_verify_coz — generic path with a 4-bit signed window over a COMMON-Z table of Q.
+// k_verify_coz — keys-per-item path with a 4-bit signed window over a COMMON-Z table of Q.
 // The eight multiples k*Q are brought to one shared Z (Zc), so a table entry is 64 bytes: 2Q..8Q
 // live in shared memory (448 B per thread, bank = lane), 1Q and Zc, Zc^2, Zc^3 in a coalesced global
-// scratch (tscr[40][n]).  65 additions of 11M+3S instead of the 86 of 12M+4S a 3-bit Jacobian table
-// needs at the same single-wave occupancy (7 blocks of 64 threads per SM).
-// LOCKSTEP: one big block per SM with a block barrier per window, so the warps of an SM progress
-// together and finish together (a single-wave launch otherwise ends with stragglers issuing alone).
-template <class C, int BLOCK, int MINB, bool LOCKSTEP = false>
+// scratch (tscr[.][n]).  65 additions of 11M+3S.
+// `list`/`count` (optional): the thread handles item list[t], t < *count — the items the key grouping
+// (keygroup.cuh) left on this path.  Items whose key or (r, s) are invalid reject at once.
+template <class C, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_verify_coz(uint32_t n, const uint8_t *__restrict__ qx_be, const uint8_t *__restrict__ qy_be,
-                                                             const uint8_t *__restrict__ r_be, const uint16_t *__restrict__ gidx,
-                                                             const int8_t *__restrict__ digits, const uint8_t *__restrict__ flags,
+                                                             const uint8_t *__restrict__ r_be, const uint32_t *__restrict__ uw,
+                                                             const uint8_t *__restrict__ flags,
                                                              const uint4 *__restrict__ gtab, uint32_t *__restrict__ tscr,
-                                                             uint8_t *__restrict__ ok_out) {
+                                                             uint8_t *__restrict__ ok_out, const uint32_t *__restrict__ list,
+                                                             const uint32_t *__restrict__ count) {
     constexpr int N = C::N;
     constexpr int W = 4;
     constexpr int NWIN = Windows<32 * N, W>::COUNT;
     extern __shared__ uint32_t tab[];  // entries 2..8: [((k-2)*2 + coord)*N + limb][BLOCK]
     const uint32_t tid = threadIdx.x;
-    uint32_t idx = blockIdx.x * BLOCK + tid;
-    const bool live = idx < n;
-    if (!LOCKSTEP && !live) return;
-    if (!live) idx = n - 1;  // LOCKSTEP: surplus threads shadow the last item so every barrier is reached
+    const uint32_t t = blockIdx.x * BLOCK + tid;
+    if (t >= (list ? __ldg(count) : n)) return;  // the table is thread-private: no block-wide barrier anywhere
+    const uint32_t idx = list ? __ldg(list + t) : t;
 #define TAB(k, c, w) tab[((((k) - 2) * 2 + (c)) * N + (w)) * BLOCK + tid]
-#define SCR(w) tscr[(size_t)(w) * n + idx]
+#define SCR(w) tscr[(size_t)(w) * n + t]
     // scratch words: [0,2N) entry 1 (x, y) ; [2N,3N) Zc ; [3N,4N) Zc^2 ; [4N,5N) Zc^3 ; [5N, 12N) H_2..H_8
-    uint32_t pmod[N], one[N];
-    C::get_p(pmod);
+    uint32_t one[N];
     C::get_one(one);
-    bool good = flags[idx] != 0;
     {
-        uint32_t x[N], y[N], rr[N], qxm[N], qym[N];
-        load_be<N>(x, qx_be + (size_t)idx * C::BYTES);
-        load_be<N>(y, qy_be + (size_t)idx * C::BYTES);
-        good = good && mp_lt<N>(x, pmod) && mp_lt<N>(y, pmod);
-        C::get_rr_p(rr);
-        C::fmul(qxm, x, rr);
-        C::fmul(qym, y, rr);
-        {
-            uint32_t lhs[N], rhs[N], t[N], b[N];
-            C::fsqr(lhs, qym);
-            C::fsqr(t, qxm);
-            C::fmul(rhs, t, qxm);
-            C::fsub(rhs, rhs, qxm); C::fsub(rhs, rhs, qxm); C::fsub(rhs, rhs, qxm);
-            C::get_b(b);
-            C::fadd(rhs, rhs, b);
-            good = good && mp_eq<N>(lhs, rhs);
-        }
+        uint32_t qxm[N], qym[N];
+        const bool good = load_key<C>(qxm, qym, qx_be, qy_be, idx) && flags[idx] != 0;
+        if (!good) { ok_out[idx] = 0; return; }
         // forward: T_k = k*Q in Jacobian; keep (X_k, Y_k) and the ratio H_k = Z_k / Z_{k-1}
         Jac<C> P;
         mp_copy<N>(P.X, qxm); mp_copy<N>(P.Y, qym); mp_copy<N>(P.Z, one);
@@ -562,7 +367,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_verify_coz(uint32_t n, const ui
 #pragma unroll 1
             for (int k = 0; k < W; k++) pt_double<C>(acc);
         }
-        int d = digits[(size_t)win * n + idx];
+        const int d = booth_digit_u2<C, W>(uw, n, idx, win);
         bool neg = d < 0, skip = d == 0;
         int e = neg ? -d : d;          // 0..8
         int es = e < 2 ? 2 : e;        // shared-memory slot actually read
@@ -576,66 +381,96 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_verify_coz(uint32_t n, const ui
             zc[i] = SCR(2 * N + i); zc2[i] = SCR(3 * N + i); zc3[i] = SCR(4 * N + i);
         }
         pt_add_m<C, 2>(acc, x2, y2, zc, zc2, zc3, neg, skip);
-        if (LOCKSTEP) __syncthreads();
     }
-    {
-        constexpr int EU4 = 2 * N / 4;
-        uint32_t gx[N], gy[N];
-        uint32_t gb = gidx[idx];
-        load_affine<C>(gx, gy, gtab + (size_t)gb * EU4);
-#pragma unroll 1
-        for (int win = 0; win < C::GWINS; win++) {
-            uint32_t ngx[N], ngy[N];
-            uint32_t ngb = 0;
-            if (win + 1 < C::GWINS) {
-                ngb = gidx[(size_t)(win + 1) * n + idx];
-                load_affine<C>(ngx, ngy, gtab + (((size_t)(win + 1) << C::GW) + ngb) * EU4);
-            }
-            pt_add<C, true>(acc, gx, gy, one, false, gb == 0);
-            if (win + 1 < C::GWINS) { mp_copy<N>(gx, ngx); mp_copy<N>(gy, ngy); gb = ngb; }
-            if (LOCKSTEP) __syncthreads();
-        }
-    }
+    add_u1G<C>(acc, uw, n, idx, gtab);
 #undef TAB
 #undef SCR
-    bool match = false;
-    if (!mp_is_zero<N>(acc.Z)) {
-        uint32_t zz[N], r[N], rr[N], rm[N], lhs[N], pmn[N];
-        C::fsqr(zz, acc.Z);
-        load_be<N>(r, r_be + (size_t)idx * C::BYTES);
-        C::get_rr_p(rr);
-        C::fmul(rm, r, rr);
-        C::fmul(lhs, rm, zz);
-        match = mp_eq<N>(lhs, acc.X);
-        C::get_p_minus_n(pmn);
-        if (!match && mp_lt<N>(r, pmn)) {
-            uint32_t r2[N], nmod[N];
-            C::get_n(nmod);
-            mp_add<N>(r2, r, nmod);
-            C::fmul(rm, r2, rr);
-            C::fmul(lhs, rm, zz);
-            match = mp_eq<N>(lhs, acc.X);
-        }
-    }
-    if (live) ok_out[idx] = (good && match) ? 1 : 0;
+    ok_out[idx] = final_check<C>(acc, r_be, idx) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_verify_keyed_warp — ONE SIGNATURE PER WARP, for small batches (latency path of the registered-key
-// entry points).  The BYTES + GWINS comb additions of a signature are independent, so each lane adds
-// its one or two table points and the 32 partial sums are tree-reduced with warp shuffles (5 general
+// Fixed-base path: per-key table KT[kid][win][e-1] = e * 2^(W*win) * Q_kid for e = 1..2^(W-1), affine Montgomery
+// form (keygroup.cuh builds it).  u2*Q = sum over the NWIN Booth digits of u2: no doublings at all.
+template <int BITS, int W>
+struct KeyTab {
+    static constexpr int NWIN = Windows<BITS, W>::COUNT;
+    static constexpr int ENT = Windows<BITS, W>::ENTRIES;
+    static constexpr size_t POINTS = (size_t)NWIN * ENT;  // affine points per key
+};
+
+// REG = true: registered keys (sbv_set_keys): the key of item i is kidmap[slot[i]].
+// REG = false: keys grouped on the fly: the key of item i is kidmap[i] (>= 0 for every listed item).
+template <class C, int W, int BLOCK, int MINB, bool REG>
+__global__ void __launch_bounds__(BLOCK, MINB) k_verify_kt(uint32_t n, const uint32_t *__restrict__ slot, const int32_t *__restrict__ kidmap,
+                                                            uint32_t n_slots, const uint8_t *__restrict__ keyflags,
+                                                            const uint8_t *__restrict__ r_be, const uint32_t *__restrict__ uw,
+                                                            const uint8_t *__restrict__ flags, const uint4 *__restrict__ gtab,
+                                                            const uint4 *__restrict__ ktab, uint8_t *__restrict__ ok_out,
+                                                            const uint32_t *__restrict__ list, const uint32_t *__restrict__ count) {
+    constexpr int N = C::N;
+    constexpr int EU4 = 2 * N / 4;  // uint4 per table entry
+    using KT = KeyTab<32 * N, W>;
+    const uint32_t t = blockIdx.x * BLOCK + threadIdx.x;
+    if (t >= (list ? __ldg(count) : n)) return;
+    const uint32_t idx = list ? __ldg(list + t) : t;
+    bool good = flags[idx] != 0;
+    int32_t kid;
+    if (REG) {
+        const uint32_t sl = slot[idx];
+        kid = sl < n_slots ? kidmap[sl] : -1;
+    } else {
+        kid = kidmap[idx];
+    }
+    good = good && kid >= 0 && keyflags[kid < 0 ? 0 : kid] != 0;
+    if (!good) { ok_out[idx] = 0; return; }
+    const uint4 *kt = ktab + (size_t)kid * KT::POINTS * EU4;
+    uint32_t one[N];
+    C::get_one(one);
+    Jac<C> acc;
+    mp_copy<N>(acc.X, one);
+    mp_copy<N>(acc.Y, one);
+#pragma unroll
+    for (int i = 0; i < N; i++) acc.Z[i] = 0;
+    // software pipeline: the table entry of the next window is in flight while the current one is added
+    uint32_t kx[N], ky[N];
+    int d = booth_digit_u2<C, W>(uw, n, idx, 0);
+    {
+        const int e = d < 0 ? -d : d;
+        load_affine<C>(kx, ky, kt + (size_t)(e ? e - 1 : 0) * EU4);
+    }
+#pragma unroll 1
+    for (int win = 0; win < KT::NWIN; win++) {
+        uint32_t nkx[N], nky[N];
+        int nd = 0;
+        if (win + 1 < KT::NWIN) {
+            nd = booth_digit_u2<C, W>(uw, n, idx, win + 1);
+            const int e = nd < 0 ? -nd : nd;
+            load_affine<C>(nkx, nky, kt + ((size_t)(win + 1) * KT::ENT + (e ? e - 1 : 0)) * EU4);
+        }
+        pt_add<C, true>(acc, kx, ky, one, d < 0, d == 0);
+        if (win + 1 < KT::NWIN) { mp_copy<N>(kx, nkx); mp_copy<N>(ky, nky); d = nd; }
+    }
+    add_u1G<C>(acc, uw, n, idx, gtab);
+    ok_out[idx] = final_check<C>(acc, r_be, idx) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_verify_kt_warp — ONE SIGNATURE PER WARP, for small batches (latency path of the registered-key
+// entry points).  The NWIN + GWINS table additions of a signature are independent, so each lane adds
+// its two or three table points and the 32 partial sums are tree-reduced with warp shuffles (5 general
 // additions).  Per signature this issues ~6x the instructions of the thread-per-signature kernel, but
-// its dependent chain is 2 + 5 additions instead of 48: ~0.05 ms instead of ~0.3 ms for a lone
-// signature.  Chosen by the launcher when the batch cannot fill the machine anyway.
-template <class C>
-__global__ void __launch_bounds__(128) k_verify_keyed_warp(uint32_t n, const uint32_t *__restrict__ slot, const int32_t *__restrict__ slot2local,
-                                                           uint32_t n_slots, const uint8_t *__restrict__ keyflags,
-                                                           const uint8_t *__restrict__ r_be, const uint16_t *__restrict__ gidx,
-                                                           const uint8_t *__restrict__ qidx, const uint8_t *__restrict__ flags,
-                                                           const uint4 *__restrict__ gtab, const uint4 *__restrict__ ktab,
-                                                           uint8_t *__restrict__ ok_out) {
+// its dependent chain is 3 + 5 additions instead of NWIN + GWINS.  Chosen by the launcher when the batch
+// cannot fill the machine anyway.
+template <class C, int W>
+__global__ void __launch_bounds__(128) k_verify_kt_warp(uint32_t n, const uint32_t *__restrict__ slot, const int32_t *__restrict__ slot2local,
+                                                        uint32_t n_slots, const uint8_t *__restrict__ keyflags,
+                                                        const uint8_t *__restrict__ r_be, const uint32_t *__restrict__ uw,
+                                                        const uint8_t *__restrict__ flags,
+                                                        const uint4 *__restrict__ gtab, const uint4 *__restrict__ ktab,
+                                                        uint8_t *__restrict__ ok_out) {
     constexpr int N = C::N;
     constexpr int EU4 = 2 * N / 4;
+    using KT = KeyTab<32 * N, W>;
     const uint32_t idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // signature = warp
     const uint32_t lane = threadIdx.x & 31;
     if (idx >= n) return;
@@ -645,7 +480,7 @@ __global__ void __launch_bounds__(128) k_verify_keyed_warp(uint32_t n, const uin
     good = good && local >= 0;
     if (local < 0) local = 0;
     good = good && keyflags[local] != 0;
-    const uint4 *kt = ktab + (size_t)local * C::BYTES * 256 * EU4;
+    const uint4 *kt = ktab + (size_t)local * KT::POINTS * EU4;
     uint32_t one[N];
     C::get_one(one);
     Jac<C> acc;
@@ -654,19 +489,20 @@ __global__ void __launch_bounds__(128) k_verify_keyed_warp(uint32_t n, const uin
 #pragma unroll
     for (int i = 0; i < N; i++) acc.Z[i] = 0;
 #pragma unroll 1
-    for (int it = 0; it < (C::BYTES + 31) / 32; it++) {  // u2 * Q_k : this lane's windows
+    for (int it = 0; it < (KT::NWIN + 31) / 32; it++) {  // u2 * Q_k : this lane's windows
         const int win = it * 32 + (int)lane;
-        const bool live = win < C::BYTES;
-        const uint32_t b = live ? qidx[(size_t)win * n + idx] : 0u;
+        const bool live = win < KT::NWIN;
+        const int d = live ? booth_digit_u2<C, W>(uw, n, idx, win) : 0;
+        const int e = d < 0 ? -d : d;
         uint32_t x2[N], y2[N];
-        load_affine<C>(x2, y2, kt + ((size_t)(live ? win : 0) * 256 + b) * EU4);
-        pt_add<C, true>(acc, x2, y2, one, false, b == 0);
+        load_affine<C>(x2, y2, kt + ((size_t)(live ? win : 0) * KT::ENT + (e ? e - 1 : 0)) * EU4);
+        pt_add<C, true>(acc, x2, y2, one, d < 0, d == 0);
     }
 #pragma unroll 1
     for (int it = 0; it < (C::GWINS + 31) / 32; it++) {  // u1 * G
         const int win = it * 32 + (int)lane;
         const bool live = win < C::GWINS;
-        const uint32_t b = live ? gidx[(size_t)win * n + idx] : 0u;
+        const uint32_t b = live ? comb_digit_u1<C>(uw, n, idx, win) : 0u;
         uint32_t x2[N], y2[N];
         load_affine<C>(x2, y2, gtab + (((size_t)(live ? win : 0) << C::GW) + b) * EU4);
         pt_add<C, true>(acc, x2, y2, one, false, b == 0);
@@ -683,26 +519,7 @@ __global__ void __launch_bounds__(128) k_verify_keyed_warp(uint32_t n, const uin
         pt_add<C, false>(acc, x2, y2, z2, false, mp_is_zero<N>(z2));
     }
     if (lane != 0) return;
-    bool match = false;
-    if (!mp_is_zero<N>(acc.Z)) {
-        uint32_t zz[N], r[N], rr[N], rm[N], lhs[N], pmn[N];
-        C::fsqr(zz, acc.Z);
-        load_be<N>(r, r_be + (size_t)idx * C::BYTES);
-        C::get_rr_p(rr);
-        C::fmul(rm, r, rr);
-        C::fmul(lhs, rm, zz);
-        match = mp_eq<N>(lhs, acc.X);
-        C::get_p_minus_n(pmn);
-        if (!match && mp_lt<N>(r, pmn)) {
-            uint32_t r2[N], nmod[N];
-            C::get_n(nmod);
-            mp_add<N>(r2, r, nmod);
-            C::fmul(rm, r2, rr);
-            C::fmul(lhs, rm, zz);
-            match = mp_eq<N>(lhs, acc.X);
-        }
-    }
-    ok_out[idx] = (good && match) ? 1 : 0;
+    ok_out[idx] = (good && final_check<C>(acc, r_be, idx)) ? 1 : 0;
 }
 
 }  // namespace sbv

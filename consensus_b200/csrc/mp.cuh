@@ -7,11 +7,32 @@
 // N*N wide MADs + 2N carry words + one 2N-limb add per product.
 #pragma once
 #include <stdint.h>
+#include "hostsim.h"
 
 namespace sbv {
 
 #define SBV_DEV __device__ __forceinline__
 
+#if defined(SBV_HOSTSIM) && !defined(__CUDACC__)
+// CPU emulation of the PTX carry-flag primitives (tests only, see hostsim.h): one thread-local CC.CF.
+static thread_local uint32_t sbv_cc = 0;
+SBV_DEV uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; sbv_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
+SBV_DEV uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + sbv_cc; sbv_cc = (uint32_t)(t >> 32); return (uint32_t)t; }
+SBV_DEV uint32_t addc(uint32_t a, uint32_t b) { return a + b + sbv_cc; }
+SBV_DEV uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; sbv_cc = (uint32_t)(t >> 63); return (uint32_t)t; }
+SBV_DEV uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - sbv_cc; sbv_cc = (uint32_t)(t >> 63); return (uint32_t)t; }
+SBV_DEV uint32_t subc(uint32_t a, uint32_t b) { return a - b - sbv_cc; }
+SBV_DEV void mad_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+    const uint64_t p = (uint64_t)a * b;
+    uint64_t t = (uint64_t)lo + (uint32_t)p; lo = (uint32_t)t;
+    t = (uint64_t)hi + (uint32_t)(p >> 32) + (t >> 32); hi = (uint32_t)t; sbv_cc = (uint32_t)(t >> 32);
+}
+SBV_DEV void madc_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
+    const uint64_t p = (uint64_t)a * b;
+    uint64_t t = (uint64_t)lo + (uint32_t)p + sbv_cc; lo = (uint32_t)t;
+    t = (uint64_t)hi + (uint32_t)(p >> 32) + (t >> 32); hi = (uint32_t)t; sbv_cc = (uint32_t)(t >> 32);
+}
+#else
 SBV_DEV uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 SBV_DEV uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 SBV_DEV uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
@@ -27,6 +48,7 @@ SBV_DEV void mad_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
 SBV_DEV void madc_wide_cc(uint32_t &lo, uint32_t &hi, uint32_t a, uint32_t b) {
     asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
 }
+#endif
 
 // r[0..2N) = a[0..N) * b[0..N)
 template <int N>

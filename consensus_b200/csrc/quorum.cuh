@@ -19,17 +19,17 @@ namespace sbv {
 __global__ void k_quorum_count(uint32_t n_votes, const uint32_t *__restrict__ instance, const uint16_t *__restrict__ sender,
                                const uint16_t *__restrict__ signer, const uint8_t *__restrict__ digest_match,
                                const uint8_t *__restrict__ ok, const uint16_t *__restrict__ self_id,
-                               uint32_t n_instances, uint32_t *__restrict__ valid_count) {
+                               uint32_t inst_base, uint32_t n_instances, uint32_t *__restrict__ valid_count) {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_votes) return;
-    const uint32_t inst = instance[v];
+    const uint32_t inst = instance[v] - inst_base;  // a device holds the instances [inst_base, inst_base + n_instances)
     if (inst >= n_instances) return;
     const uint16_t snd = sender[v];
     if (signer[v] != snd) return;
     if (self_id && self_id[inst] == snd) return;
-    if (!(digest_match[v] && ok[v])) return;  // registered or not, it cannot count
+    if (!(digest_match[v] && (!ok || ok[v]))) return;  // registered or not, it cannot count (ok == NULL: prepares carry no signature)
     for (uint32_t j = v; j-- > 0;) {
-        if (instance[j] != inst) break;
+        if (instance[j] - inst_base != inst) break;
         if (sender[j] == snd && signer[j] == snd) return;  // an earlier registered vote burnt the slot
     }
     atomicAdd(valid_count + inst, 1u);

@@ -30,9 +30,14 @@
  *    coordinates < p; r, s in [1, n-1]; e = leftmost min(len, 32|48) digest bytes; R = (e/s)G +
  *    (r/s)Q must not be infinity; accept iff R.x mod n == r.  No low-S rule.
  *  - Thread-safe and re-entrant: the CUDA device is set explicitly per call, so calls may come from any
- *    OS thread (cgo).  sbv_verify_batch / sbv_verify_registered / sbv_hash_verify_registered each own a
- *    lane (stream, buffers, pinned staging) for the duration of the call — two calls proceed concurrently
- *    and overlap their copies and kernels; a third waits.  The other entry points serialise on the engine lock.
+ *    OS thread (cgo).  Every host-buffer entry point owns a lane (stream, device buffers, pinned staging) for
+ *    the duration of the call — three calls proceed concurrently and overlap their copies and kernels; a
+ *    fourth waits.  On every return path, faults included, the lane has been drained: no copy into or out of
+ *    the caller's buffers is in flight after the call returns, and on a fault the output arrays are untouched
+ *    or partially written but never read as verdicts (the caller fail-stops).
+ *  - Keys that repeat inside a keys-per-item batch are detected on the device and verified against a per-key
+ *    fixed-base table built on the spot (SBV_GROUP_THRESHOLD, default 16 occurrences; 0 disables): the verdicts
+ *    are the same bit for bit, only cheaper.
  *  - There is no CPU fallback: without a usable CUDA device sbv_create fails.
  */
 #ifndef SBV_H
@@ -59,7 +64,8 @@ enum {
  * engine shards every batch across the devices and gathers the packed verdict bitmask with NCCL. */
 int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out);
 void sbv_destroy(sbv_engine *e);
-/* Human-readable description of the last fault on this engine (valid until the next call). */
+/* Human-readable description of the last fault on this engine (a thread-local copy: valid until the calling
+ * thread's next sbv_last_error). */
 const char *sbv_last_error(const sbv_engine *e);
 int sbv_device_count(const sbv_engine *e);
 
@@ -105,13 +111,32 @@ int sbv_quorum(sbv_engine *e, size_t n_votes, const uint32_t *instance, const ui
                const uint16_t *signer, const uint8_t *digest_match, const uint8_t *ok, size_t n_instances,
                const uint16_t *self_id, uint32_t threshold, uint32_t *valid_count, uint8_t *reached);
 
+/* Prepare collection in batch form (View.processPrepares, view.go:441-517): prepares carry no signature; the
+ * first prepare of a sender burns its slot (util.go:130-143) and counts iff digest_match (view.go:452-459);
+ * reached[i] = match_count[i] >= threshold (the caller passes Quorum-1, view.go:446). */
+int sbv_prepare_quorum(sbv_engine *e, size_t n_votes, const uint32_t *instance, const uint16_t *sender,
+                       const uint8_t *digest_match, size_t n_instances, const uint16_t *self_id, uint32_t threshold,
+                       uint32_t *match_count, uint8_t *reached);
+
+/* Commit-vote verification AND quorum collection in one call (verifyVote + processCommits, view.go:519-551,
+ * 827-849; BASELINE configs[3]).  The n_votes signatures (SoA as in sbv_verify_batch) are verified, the verdicts stay
+ * on the device and feed the distinct-signer count of sbv_quorum.  Votes must be grouped by instance with
+ * non-decreasing instance ids, in arrival order inside an instance.  A multi-device engine shards BY INSTANCE so that
+ * every count is local; the packed verdict mask and the packed `reached` mask travel in one NCCL all-gather.
+ * Outputs: ok[n_votes], valid_count[n_instances], reached[n_instances]. */
+int sbv_verify_quorum(sbv_engine *e, uint8_t curve, size_t n_votes, const uint8_t *r, const uint8_t *s, const uint8_t *qx,
+                      const uint8_t *qy, const uint8_t *digest, uint8_t digest_len, const uint32_t *instance,
+                      const uint16_t *sender, const uint16_t *signer, const uint8_t *digest_match, size_t n_instances,
+                      const uint16_t *self_id, uint32_t threshold, uint8_t *ok, uint32_t *valid_count, uint8_t *reached);
+
 /* computeQuorum(n) -> (q, f), internal/bft/util.go:183-187. */
 void sbv_compute_quorum(uint64_t n, uint32_t *q, uint32_t *f);
 
 /* Consenter key registry.  Keys are configuration in the reference: they change only with a
  * reconfiguration, i.e. a new VerificationSequence (dependencies.go:65-66).  sbv_set_keys replaces
  * the registry and precomputes, on every device, a fixed-base comb table per key
- * (32*256 affine points = 512 KiB per P-256 key); slot i of the registry is key i of this call.
+ * (8-bit signed windows: 33 x 128 affine points = 264 KiB per P-256 key, a few milliseconds for a thousand keys);
+ * slot i of the registry is key i of this call.
  * xy = n * 96 bytes: X and Y in 48-byte slots (P-256 values right-aligned). */
 int sbv_set_keys(sbv_engine *e, uint64_t verification_seq, size_t n, const uint64_t *ids, const uint8_t *curve,
                  const uint8_t *xy);
@@ -130,11 +155,32 @@ int sbv_verify_registered_device(sbv_engine *e, int device_index, uint8_t curve,
                                  const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_digest, uint8_t digest_len,
                                  uint8_t *d_ok, void *cuda_stream);
 
+/* ---- one process per GPU (a Go host may run one node process per device; bench.py does under torchrun) ----
+ * The engine of every process is one RANK; the only exchange is the all-gather of packed verdict / quorum bitmasks
+ * over NCCL (NVLink / NVSwitch).  Rank 0 calls sbv_comm_unique_id and ships the 128 bytes to the others (any side
+ * channel); every rank then calls sbv_comm_init_rank, which adds one CHANNEL (communicator) and returns its index.
+ * The collectives of a channel must be issued in the same order on every rank, so concurrent caller threads take
+ * one channel each (create as many as there are threads, in the same order on every rank). */
+int sbv_comm_unique_id(uint8_t *id128);
+int sbv_comm_init_rank(sbv_engine *e, const uint8_t *id128, int nranks, int rank);
+int sbv_comm_ranks(const sbv_engine *e);
+/* Device form: packs n verdict bytes into a bitmask and all-gathers the masks of all ranks,
+ * d_mask_all[rank * ceil(n/32) + w]; enqueued on cuda_stream, not synchronised.  Every rank passes the same n. */
+int sbv_gather_verdicts_device(sbv_engine *e, int channel, const uint8_t *d_ok, size_t n, uint32_t *d_mask_all, void *cuda_stream);
+/* All-gather of `words` 32-bit words per rank, in place: the sender's words sit at d_all + rank * words. */
+int sbv_gather_words_device(sbv_engine *e, int channel, uint32_t *d_all, size_t words, void *cuda_stream);
+/* Host form: sbv_verify_batch for this rank's n items + the gather: ok[n] = this rank's verdict bytes,
+ * mask_all[nranks * ceil(n/32)] = the packed verdicts of every rank. */
+int sbv_verify_batch_ranked(sbv_engine *e, int channel, uint8_t curve, size_t n, const uint8_t *r, const uint8_t *s,
+                            const uint8_t *qx, const uint8_t *qy, const uint8_t *digest, uint8_t digest_len, uint8_t *ok,
+                            uint32_t *mask_all);
+
 /* Introspection for benchmarks: number of kernel launches issued by this engine so far. */
 uint64_t sbv_kernel_launches(const sbv_engine *e);
-/* Optional CUDA-event timing of the two kernels of every verify launch (off by default).
- * sbv_profile_read sums the recorded intervals in milliseconds over all devices and resets; the
- * caller synchronises the streams it used first. */
+/* Optional CUDA-event timing inside every verify launch (off by default).  sbv_profile_read sums, over all
+ * devices, prep_ms = launch start .. end of the scalar preparation (includes the key grouping) and verify_ms = the
+ * dominant verify kernel alone (the fixed-base kernel when keys were grouped, the generic one otherwise), and
+ * resets; the caller synchronises the streams it used first. */
 int sbv_profile_enable(sbv_engine *e, int on);
 int sbv_profile_read(sbv_engine *e, double *prep_ms, double *verify_ms, uint64_t *n_launch_pairs);
 /* Peak-rate probe: dependent-free IMAD.WIDE.U32 loop on device 0; returns MAC32/s (0 on fault). */

@@ -272,6 +272,33 @@ def count_commit_votes(votes, self_id=None):
     return valid
 
 
+def count_commit_votes_batch(instance, sender, signer, digest_match, sig_ok, n_instances, threshold, self_id=None):
+    """count_commit_votes over a stream of votes grouped by instance (arrival order inside an instance).
+    Returns (valid_count[n_instances], reached[n_instances]) as Python lists -> numpy via the caller;
+    reached = valid_count >= threshold (the caller passes Quorum-1, view.go:531).  self_id: per-instance ids or None."""
+    import numpy as np
+    cnt = np.zeros(n_instances, np.uint32)
+    voted = {}
+    inst_l, snd_l, sig_l = [int(x) for x in instance], [int(x) for x in sender], [int(x) for x in signer]
+    dm_l, ok_l = [int(x) for x in digest_match], [int(x) for x in sig_ok]
+    sid = None if self_id is None else [int(x) for x in self_id]
+    for v in range(len(inst_l)):
+        i, snd = inst_l[v], snd_l[v]
+        if i >= n_instances:
+            continue
+        if sid is not None and snd == sid[i]:
+            continue
+        if sig_l[v] != snd:
+            continue
+        seen = voted.setdefault(i, set())
+        if snd in seen:
+            continue
+        seen.add(snd)
+        if dm_l[v] and ok_l[v]:
+            cnt[i] += 1
+    return cnt, (cnt >= threshold).astype(np.uint8)
+
+
 def validate_last_decision_sigs(signers, sig_ok, quorum: int) -> bool:
     """viewchanger.go:697-727: >= quorum signatures present; duplicates of a signer skipped; any
     invalid (non-duplicate) signature fails the decision; valid distinct >= quorum."""

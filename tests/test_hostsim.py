@@ -1,0 +1,160 @@
+"""CPU simulation of the DEVICE code (tools/hostsim: mp.cuh / curve.cuh / kernels.cuh / keygroup.cuh compiled with g++,
+PTX carry-flag primitives emulated, one simulated thread at a time) against Python big integers and the oracle.
+
+This is how limb-level arithmetic and the kernels' control flow are checked without a GPU; the `-m gpu` tests run the
+same checks on the real thing.  The simulation is test infrastructure — libsbv.so has no CPU path."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import corpus
+from oracle import ecdsa_ref as ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HS_DIR = os.path.join(ROOT, "tools", "hostsim")
+
+
+@pytest.fixture(scope="module")
+def hs():
+    subprocess.check_call(["make", "-s", "-C", HS_DIR, "libhostsim.so"])
+    return C.CDLL(os.path.join(HS_DIR, "libhostsim.so"))
+
+
+def _limbs(vals, N):
+    out = np.zeros((len(vals), 2 * N), np.uint32)
+    for i, pair in enumerate(vals):
+        for h, v in enumerate(pair):
+            for k in range(N):
+                out[i, h * N + k] = (v >> (32 * k)) & 0xFFFFFFFF
+    return out
+
+
+def _ints(arr, N):
+    return [tuple(sum(int(row[h * N + k]) << (32 * k) for k in range(N)) for h in range(2)) for row in arr]
+
+
+def _run(hs, curve, op, a, b):
+    N = 8 if curve == 0 else 12
+    A, B = _limbs(a, N), _limbs(b, N)
+    out = np.zeros_like(A)
+    p32 = lambda x: x.ctypes.data_as(C.POINTER(C.c_uint32))
+    assert hs.hs_debug_op(C.c_int(curve), C.c_int(op), C.c_size_t(len(a)), p32(A), p32(B), p32(out)) == 0
+    return _ints(out, N)
+
+
+def _edge_values(m, rng, count):
+    F = (1 << 32) - 1
+    vals = [0, 1, 2, m - 1, m - 2, (m - 1) // 2, F, 1 << 32, (1 << 64) - 1, 1 << 96, (1 << 224) % m, m >> 1,
+            0xFFFFFFFF00000000FFFFFFFF00000000FFFFFFFF00000000FFFFFFFF00000000 % m, ((1 << 96) - 1), (m - (1 << 96)) % m,
+            (m - (1 << 192)) % m, ((1 << 256) - 1) % m, ((1 << 255) + 12345) % m]
+    vals += [int.from_bytes(rng.bytes(48), "big") % m for _ in range(count)]
+    # values with long runs of ones / zeros in single limbs: carry-chain stress
+    for _ in range(count // 4):
+        v = 0
+        for k in range(12):
+            v |= int(rng.choice([0, F, 1, F - 1, 0x80000000, int(rng.integers(0, F))])) << (32 * k)
+        vals.append(v % m)
+    return vals
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_field_ops(hs, curve):
+    c = ref.CURVES[curve]
+    N = c.size // 4
+    R = 1 << (32 * N)
+    rng = np.random.default_rng(curve + 11)
+    for m, mulop in [(c.p, 0), (c.n, 3)]:
+        xs = _edge_values(m, rng, 1500)
+        ys = list(reversed(_edge_values(m, rng, 1500)))
+        a = [(x, 0) for x in xs]; b = [(y, 0) for y in ys]
+        Rinv = pow(R, -1, m)
+        assert [g[0] for g in _run(hs, curve, mulop, a, b)] == [x * y * Rinv % m for x, y in zip(xs, ys)]
+        if m == c.p:
+            assert [g[0] for g in _run(hs, curve, 9, a, b)] == [x * x * Rinv % m for x in xs]
+            assert [g[0] for g in _run(hs, curve, 1, a, b)] == [(x + y) % m for x, y in zip(xs, ys)]
+            assert [g[0] for g in _run(hs, curve, 2, a, b)] == [(x - y) % m for x, y in zip(xs, ys)]
+    xs = [v for v in _edge_values(c.p, rng, 10) if v]
+    got = _run(hs, curve, 4, [(x * R % c.p, 0) for x in xs], [(0, 0)] * len(xs))
+    assert [g[0] for g in got] == [pow(x, -1, c.p) * R % c.p for x in xs]
+    xs = [v for v in _edge_values(c.n, rng, 200) if v]
+    xs += [pow(2, k, c.n) for k in (1, 31, 32, 33, 63, 64, 65, 96, 128, 255, 256, 300, 383)]
+    got = _run(hs, curve, 8, [(x * R % c.n, 0) for x in xs], [(0, 0)] * len(xs))
+    assert [g[0] for g in got] == [pow(x, -1, c.n) * R % c.n for x in xs]
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_group_law(hs, curve):
+    c = ref.CURVES[curve]
+    G = (c.gx, c.gy)
+    ks = [1, 2, 3, 4, 5, 7, 8, 255, c.n - 1, c.n - 2, 2**100 + 3]
+    pts = [ref.scalar_mult(c, k, G) for k in ks]
+    assert _run(hs, curve, 5, pts, pts) == [ref._add(c, P, P) for P in pts]
+    pairs = [(P, Q) for P in pts for Q in pts]
+    want = [ref._add(c, P, Q) or (0, 0) for P, Q in pairs]
+    assert _run(hs, curve, 7, [p for p, _ in pairs], [q for _, q in pairs]) == want
+    want = [ref._add(c, ref._add(c, P, P), Q) or (0, 0) for P, Q in pairs]
+    assert _run(hs, curve, 6, [p for p, _ in pairs], [q for _, q in pairs]) == want
+
+
+def _p8(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def _verify(hs, curve, b, grouped=None):
+    n = b["r"].shape[0]
+    ok = np.full(n, 7, np.uint8)
+    f = [np.ascontiguousarray(b[k]) for k in ("r", "s", "qx", "qy", "digest")]
+    dlen = f[4].size // n
+    if grouped is None:
+        assert hs.hs_verify(C.c_int(curve), C.c_size_t(n), *map(_p8, f), C.c_uint32(dlen), _p8(ok)) == 0
+        return ok
+    thr, maxk = grouped
+    stats = np.zeros(3, np.uint32)
+    assert hs.hs_verify_grouped(C.c_int(curve), C.c_size_t(n), *map(_p8, f), C.c_uint32(dlen), C.c_uint32(thr), C.c_uint32(maxk), _p8(ok),
+                                stats.ctypes.data_as(C.POINTER(C.c_uint32))) == 0
+    return ok, stats
+
+
+def test_verify_generic_kernel_p256(hs):
+    """k_prep + k_verify_coz (the kernels of the product, simulated) on a corrupted corpus: every class of the
+    corpus, bit-exact with the oracle."""
+    b = corpus.make_batch(oracle.P256, n=192, K=8, seed=21, corrupt_rate=3)
+    want = oracle.verify_batch(oracle.P256, b["r"], b["s"], b["qx"], b["qy"], b["digest"])
+    assert 0 < int(want.sum()) < want.size
+    assert np.array_equal(_verify(hs, 0, b), want)
+
+
+def test_verify_generic_kernel_p384(hs):
+    b = corpus.make_batch(oracle.P384, n=48, K=4, seed=22, corrupt_rate=3)
+    want = oracle.verify_batch(oracle.P384, b["r"], b["s"], b["qx"], b["qy"], b["digest"])
+    assert np.array_equal(_verify(hs, 1, b), want)
+
+
+@pytest.mark.parametrize("thr,maxk", [(4, 64), (1, 64), (4, 3), (1000, 64)])
+def test_verify_grouped_p256(hs, thr, maxk):
+    """Key grouping + on-the-fly per-key tables + fixed-base kernel, with the generic kernel for the rest: same
+    verdicts as the oracle whatever the threshold / table capacity (all keys grouped, capacity exhausted, nothing
+    grouped)."""
+    b = corpus.make_batch(oracle.P256, n=256, K=8, seed=23, corrupt_rate=3)
+    want = oracle.verify_batch(oracle.P256, b["r"], b["s"], b["qx"], b["qy"], b["digest"])
+    got, stats = _verify(hs, 0, b, grouped=(thr, maxk))
+    assert np.array_equal(got, want)
+    assert int(stats[1]) + int(stats[2]) == 256
+    if thr == 1000:
+        assert int(stats[1]) == 0
+    if thr == 1 and maxk == 64:
+        assert int(stats[2]) == 0          # every key (also the corrupted, off-curve ones) got a slot; invalid ones reject by flag
+    if maxk == 3:
+        assert int(stats[0]) >= 3 and int(stats[2]) > 0
+
+
+def test_verify_grouped_p384(hs):
+    b = corpus.make_batch(oracle.P384, n=64, K=3, seed=24, corrupt_rate=3)
+    want = oracle.verify_batch(oracle.P384, b["r"], b["s"], b["qx"], b["qy"], b["digest"])
+    got, stats = _verify(hs, 1, b, grouped=(4, 16))
+    assert np.array_equal(got, want)
+    assert int(stats[1]) > 0

@@ -1,0 +1,147 @@
+// hostsim.cpp — TEST INFRASTRUCTURE: the device headers of libsbv compiled for the CPU (see csrc/hostsim.h) and
+// driven one simulated thread at a time.  tests/test_hostsim.py (-m "not gpu") compares the results with Python
+// big integers and with the oracle, so limb-level mistakes are caught without a GPU.  Not linked into libsbv.so.
+#define SBV_HOSTSIM 1
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../consensus_b200/csrc/hostsim.h"
+thread_local hostsim_dim3 threadIdx, blockIdx, blockDim, gridDim;
+namespace sbv { uint32_t tab[1 << 18]; }
+#include "../../consensus_b200/csrc/debug_ops.cuh"
+#include "../../consensus_b200/csrc/keygroup.cuh"
+
+using namespace sbv;
+
+// G comb for the simulation: T[i][b] = b * 2^(GW*i) * G, built incrementally (running sum + one batched inversion per
+// window) — the device kernel k_gtable_init builds every entry independently, which a CPU cannot afford.
+template <class C>
+static void build_comb_host(uint32_t *tab) {
+    constexpr int N = C::N;
+    const size_t per = (size_t)1 << C::GW;
+    Jac<C> base;
+    C::get_gx(base.X); C::get_gy(base.Y); C::get_one(base.Z);
+    std::vector<uint32_t> jac(per * 3 * N), pref(per * N);
+    for (int win = 0; win < C::GWINS; win++) {
+        if (win) for (int d = 0; d < C::GW; d++) pt_double<C>(base);
+        Jac<C> acc = base;
+        uint32_t run[N];
+        C::get_one(run);
+        for (size_t b = 1; b < per; b++) {
+            if (b > 1) pt_add<C, false>(acc, base.X, base.Y, base.Z, false, false);
+            memcpy(&jac[b * 3 * N], acc.X, 4 * N); memcpy(&jac[b * 3 * N + N], acc.Y, 4 * N); memcpy(&jac[b * 3 * N + 2 * N], acc.Z, 4 * N);
+            memcpy(&pref[b * N], run, 4 * N);
+            C::fmul(run, run, acc.Z);
+        }
+        uint32_t inv[N];
+        f_inv<C>(inv, run);
+        uint32_t *out = tab + ((size_t)win << C::GW) * 2 * N;
+        memset(out, 0, 2 * N * 4);
+        for (size_t b = per - 1; b >= 1; b--) {
+            uint32_t pv[N], z[N], zi[N], z2[N], z3[N], x[N], y[N];
+            memcpy(pv, &pref[b * N], 4 * N); memcpy(z, &jac[b * 3 * N + 2 * N], 4 * N);
+            memcpy(x, &jac[b * 3 * N], 4 * N); memcpy(y, &jac[b * 3 * N + N], 4 * N);
+            C::fmul(zi, inv, pv);
+            C::fmul(inv, inv, z);
+            C::fsqr(z2, zi); C::fmul(z3, z2, zi);
+            C::fmul(x, x, z2); C::fmul(y, y, z3);
+            memcpy(out + b * 2 * N, x, 4 * N); memcpy(out + b * 2 * N + N, y, 4 * N);
+        }
+    }
+}
+
+template <class F>
+static void run_grid(unsigned blocks, unsigned threads, F &&body) {
+    gridDim.x = blocks; blockDim.x = threads;
+    for (unsigned b = 0; b < blocks; b++)
+        for (unsigned t = 0; t < threads; t++) { blockIdx.x = b; threadIdx.x = t; body(); }
+}
+
+extern "C" int hs_debug_op(int curve, int op, size_t n, const uint32_t *a, const uint32_t *b, uint32_t *out) {
+    for (size_t i = 0; i < n; i++) {
+        if (curve == 0) debug_op_item<P256>(op, (uint32_t)i, a, b, out);
+        else debug_op_item<P384>(op, (uint32_t)i, a, b, out);
+    }
+    return 0;
+}
+
+// keys-per-item path: k_prep + k_verify_coz, exactly the kernels of the product, thread by thread
+template <class C, int BLOCK>
+static void verify_coz_t(uint32_t n, const uint8_t *r, const uint8_t *s, const uint8_t *qx, const uint8_t *qy, const uint8_t *dig,
+                         uint32_t dlen, const uint4 *gtab, uint8_t *ok) {
+    constexpr int N = C::N, S = 8;
+    std::vector<uint32_t> uw((size_t)2 * N * n);
+    std::vector<uint8_t> flags(n);
+    std::vector<uint32_t> tscr((size_t)12 * N * n);
+    const unsigned pthreads = (n + S - 1) / S;
+    run_grid((pthreads + 127) / 128, 128, [&] { k_prep<C, S>(n, r, s, dig, dlen, uw.data(), flags.data()); });
+    run_grid((n + BLOCK - 1) / BLOCK, BLOCK, [&] {
+        k_verify_coz<C, BLOCK, 1>(n, qx, qy, r, uw.data(), flags.data(), gtab, tscr.data(), ok, nullptr, nullptr);
+    });
+}
+
+// grouped path: k_prep, key grouping, table construction, k_verify_kt for repeated keys + k_verify_coz for the rest
+template <class C, int W>
+static void verify_grouped_t(uint32_t n, const uint8_t *r, const uint8_t *s, const uint8_t *qx, const uint8_t *qy, const uint8_t *dig,
+                             uint32_t dlen, const uint4 *gtab, uint32_t threshold, uint32_t max_keys, uint8_t *ok, uint32_t *stats) {
+    constexpr int N = C::N, S = 8;
+    using KS = KtSizes<C, W>;
+    using KT = KeyTab<32 * N, W>;
+    std::vector<uint32_t> uw((size_t)2 * N * n);
+    std::vector<uint8_t> flags(n);
+    std::vector<uint32_t> tscr((size_t)12 * N * n);
+    run_grid(((n + S - 1) / S + 127) / 128, 128, [&] { k_prep<C, S>(n, r, s, dig, dlen, uw.data(), flags.data()); });
+    uint32_t hsize = 1;
+    while (hsize < 2 * n) hsize <<= 1;
+    std::vector<uint32_t> htab(hsize, KG_EMPTY), rep(n), kcnt(n, 0), keylist(max_keys ? max_keys : 1), klist(n), glist(n), counters(4, 0);
+    std::vector<int32_t> keyid(n), item_kid(n);
+    run_grid((n + 255) / 256, 256, [&] { k_kg_insert<C>(n, qx, qy, 0x1234567u, hsize - 1, htab.data(), rep.data(), kcnt.data()); });
+    run_grid((n + 255) / 256, 256, [&] { k_kg_assign(n, rep.data(), kcnt.data(), threshold, max_keys, keyid.data(), keylist.data(), counters.data()); });
+    run_grid((n + 255) / 256, 256, [&] { k_kg_route(n, rep.data(), keyid.data(), item_kid.data(), klist.data(), glist.data(), counters.data()); });
+    const size_t cap = max_keys ? max_keys : 1;
+    std::vector<uint32_t> bases(KS::bases_words(cap)), hs(KS::hs_words(cap)), ztop(KS::ztop_words(cap)), pref(KS::ztop_words(cap)), ktab(KS::ktab_words(cap));
+    std::vector<uint8_t> kflags(cap, 0);
+    run_grid((unsigned)((cap + 63) / 64), 64, [&] { k_kt_bases<C, W>(counters.data(), (uint32_t)cap, keylist.data(), qx, qy, bases.data(), kflags.data()); });
+    run_grid((unsigned)((cap * KT::NWIN + 63) / 64), 64, [&] { k_kt_fill<C, W>(counters.data(), (uint32_t)cap, bases.data(), kflags.data(), hs.data(), ztop.data(), ktab.data()); });
+    run_grid((unsigned)((cap + 63) / 64), 64, [&] { k_kt_inv<C, W>(counters.data(), (uint32_t)cap, kflags.data(), ztop.data(), pref.data()); });
+    run_grid((unsigned)((cap * KT::NWIN + 63) / 64), 64, [&] { k_kt_final<C, W>(counters.data(), (uint32_t)cap, bases.data(), kflags.data(), hs.data(), ztop.data(), ktab.data()); });
+    run_grid((n + 63) / 64, 64, [&] {
+        k_verify_kt<C, W, 64, 1, false>(n, nullptr, item_kid.data(), 0, kflags.data(), r, uw.data(), flags.data(), gtab,
+                                        reinterpret_cast<const uint4 *>(ktab.data()), ok, klist.data(), counters.data() + 1);
+    });
+    run_grid((n + 63) / 64, 64, [&] {
+        k_verify_coz<C, 64, 1>(n, qx, qy, r, uw.data(), flags.data(), gtab, tscr.data(), ok, glist.data(), counters.data() + 2);
+    });
+    if (stats) { stats[0] = counters[0]; stats[1] = counters[1]; stats[2] = counters[2]; }
+}
+
+static std::vector<uint32_t> g_gtab[2];
+template <class C>
+static const uint4 *gtab_for(int idx) {
+    auto &g = g_gtab[idx];
+    if (g.empty()) {
+        const size_t entries = (size_t)C::GWINS << C::GW;
+        g.resize(entries * 2 * C::N);
+        // incremental construction (the device kernel builds every entry independently, far too slow for a CPU)
+        build_comb_host<C>(g.data());
+    }
+    return reinterpret_cast<const uint4 *>(g.data());
+}
+
+extern "C" int hs_verify(int curve, size_t n, const uint8_t *r, const uint8_t *s, const uint8_t *qx, const uint8_t *qy, const uint8_t *dig, uint32_t dlen,
+              uint8_t *ok) {
+    if (curve == 0) verify_coz_t<P256, 64>((uint32_t)n, r, s, qx, qy, dig, dlen, gtab_for<P256>(0), ok);
+    else verify_coz_t<P384, 64>((uint32_t)n, r, s, qx, qy, dig, dlen, gtab_for<P384>(1), ok);
+    return 0;
+}
+
+// grouped (fixed-base for repeated keys) path; stats = {keys found, items on the fixed-base path, items on the generic path}
+extern "C" int hs_verify_grouped(int curve, size_t n, const uint8_t *r, const uint8_t *s, const uint8_t *qx, const uint8_t *qy, const uint8_t *dig,
+                      uint32_t dlen, uint32_t threshold, uint32_t max_keys, uint8_t *ok, uint32_t *stats) {
+    if (curve == 0) verify_grouped_t<P256, 5>((uint32_t)n, r, s, qx, qy, dig, dlen, gtab_for<P256>(0), threshold, max_keys, ok, stats);
+    else verify_grouped_t<P384, 5>((uint32_t)n, r, s, qx, qy, dig, dlen, gtab_for<P384>(1), threshold, max_keys, ok, stats);
+    return 0;
+}
+
