@@ -24,7 +24,7 @@ SYMBOLS = [
     "sbv_probe_mad_rate", "sbv_profile_enable", "sbv_profile_read", "sbv_verify_registered",
     "sbv_verify_registered_device", "sbv_hash_verify_registered", "sbv_prepare_quorum", "sbv_verify_quorum",
     "sbv_comm_unique_id", "sbv_comm_init_rank", "sbv_comm_ranks", "sbv_gather_verdicts_device", "sbv_gather_words_device",
-    "sbv_verify_batch_ranked",
+    "sbv_verify_batch_ranked", "sbv_host_alloc", "sbv_host_free",
 ]
 
 

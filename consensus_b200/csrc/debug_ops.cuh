@@ -20,6 +20,7 @@ SBV_DEV void debug_op_item(int op, uint32_t i, const uint32_t *__restrict__ a, c
     else if (op == 3) C::nmul(r0, x, u);
     else if (op == 4) f_inv<C>(r0, x);
     else if (op == 8) n_inv<C>(r0, x);
+    else if (op == 10) p_inv<C>(r0, x);
     else if (op == 9) C::fsqr(r0, x);
     else if (op >= 5 && op <= 7) {
         // affine plain (x,y) [+ (u,v)] -> Montgomery Jacobian -> op -> affine plain

@@ -558,6 +558,13 @@ int sbv_verify_batch_ranked(sbv_engine *e, int channel, uint8_t curve, size_t n,
     return sync_lane(e, lane);
 }
 
+void *sbv_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void sbv_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 double sbv_probe_mad_rate(sbv_engine *e) {
     if (!e) return 0.0;
     std::lock_guard<std::mutex> lk(e->mu);

@@ -7,8 +7,8 @@
 namespace sbv {
 
 template <class C> struct Cfg;
-template <> struct Cfg<P256> { static constexpr int COZ_MINB = 7, KT_MINB = 7; };
-template <> struct Cfg<P384> { static constexpr int COZ_MINB = 4, KT_MINB = 4; };
+template <> struct Cfg<P256> { static constexpr int COZ_MINB = 7, KT_MINB = 7, KT_VARIANT = 0; };
+template <> struct Cfg<P384> { static constexpr int COZ_MINB = 4, KT_MINB = 4, KT_VARIANT = 0; };
 
 template <class C>
 cudaError_t op_gtable_init(uint32_t *gtab, cudaStream_t st) {
@@ -50,7 +50,9 @@ cudaError_t op_kt_build(const uint32_t *nkeys_ptr, uint32_t cap, const uint32_t 
     using KT = KeyTab<32 * C::N, W>;
     const unsigned kb = (cap + 63) / 64;
     const unsigned wb = (unsigned)(((size_t)cap * KT::NWIN + 63) / 64);
-    k_kt_bases<C, W><<<kb, 64, 0, st>>>(nkeys_ptr, cap, keylist, qx, qy, bases, keyflags);
+    static const bool bases_call = getenv("SBV_KT_BASES_CALL") != nullptr;  // A/B: out-of-line multiplications in the doubling chain
+    if (bases_call) k_kt_bases<C, W, false><<<kb, 64, 0, st>>>(nkeys_ptr, cap, keylist, qx, qy, bases, keyflags);
+    else k_kt_bases<C, W, true><<<kb, 64, 0, st>>>(nkeys_ptr, cap, keylist, qx, qy, bases, keyflags);
     k_kt_fill<C, W><<<wb, 64, 0, st>>>(nkeys_ptr, cap, bases, keyflags, hs, ztop, ktab);
     k_kt_inv<C, W><<<kb, 64, 0, st>>>(nkeys_ptr, cap, keyflags, ztop, pref);
     k_kt_final<C, W><<<wb, 64, 0, st>>>(nkeys_ptr, cap, bases, keyflags, hs, ztop, ktab);
@@ -62,16 +64,21 @@ cudaError_t op_kt_verify(int reg, int warp, uint32_t n, const uint32_t *slot, co
                          const uint8_t *keyflags, const uint8_t *r, const uint32_t *uw, const uint8_t *flags, const uint32_t *gtab,
                          const uint32_t *ktab, uint8_t *ok, const uint32_t *list, const uint32_t *count, cudaStream_t st) {
     constexpr int BLOCK = 64, MINB = Cfg<C>::KT_MINB;
-    static const bool relaxed = getenv("SBV_KT_RELAXED") != nullptr;  // A/B: one block fewer per SM, no register spills
+    static const int variant = getenv("SBV_KT_VARIANT") ? atoi(getenv("SBV_KT_VARIANT")) : Cfg<C>::KT_VARIANT;
     const uint4 *g4 = reinterpret_cast<const uint4 *>(gtab), *k4 = reinterpret_cast<const uint4 *>(ktab);
-    if (warp)
+    const unsigned blocks = (n + BLOCK - 1) / BLOCK;
+#define SBV_KT_ARGS n, slot, kidmap, n_slots, keyflags, r, uw, flags, g4, k4, ok, list, count
+    if (warp) {
         k_verify_kt_warp<C, W><<<(unsigned)(((size_t)n * 32 + 127) / 128), 128, 0, st>>>(n, slot, kidmap, n_slots, keyflags, r, uw, flags, g4, k4, ok);
-    else if (relaxed && !reg)
-        k_verify_kt<C, W, BLOCK, MINB - 1, false><<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(n, slot, kidmap, n_slots, keyflags, r, uw, flags, g4, k4, ok, list, count);
-    else if (reg)
-        k_verify_kt<C, W, BLOCK, MINB, true><<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(n, slot, kidmap, n_slots, keyflags, r, uw, flags, g4, k4, ok, list, count);
-    else
-        k_verify_kt<C, W, BLOCK, MINB, false><<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(n, slot, kidmap, n_slots, keyflags, r, uw, flags, g4, k4, ok, list, count);
+    } else if (reg) {
+        if (variant == 1) k_verify_kt<C, W, BLOCK, MINB, true, true><<<blocks, BLOCK, 0, st>>>(SBV_KT_ARGS);
+        else k_verify_kt<C, W, BLOCK, MINB, true, false><<<blocks, BLOCK, 0, st>>>(SBV_KT_ARGS);
+    } else {
+        if (variant == 1) k_verify_kt<C, W, BLOCK, MINB, false, true><<<blocks, BLOCK, 0, st>>>(SBV_KT_ARGS);          // multiplications inlined
+        else if (variant == 2) k_verify_kt<C, W, BLOCK, MINB - 1, false, true><<<blocks, BLOCK, 0, st>>>(SBV_KT_ARGS); // inlined, one block fewer per SM
+        else k_verify_kt<C, W, BLOCK, MINB, false, false><<<blocks, BLOCK, 0, st>>>(SBV_KT_ARGS);                      // multiplications out of line
+    }
+#undef SBV_KT_ARGS
     return cudaGetLastError();
 }
 

@@ -398,18 +398,33 @@ struct KeyTab {
     static constexpr size_t POINTS = (size_t)NWIN * ENT;  // affine points per key
 };
 
+// Inl<C>: the same curve with the field multiplications inlined at every call site instead of called out of line —
+// no argument marshalling and free scheduling across multiplications, at ~3 KB of code per site.  Only for loops
+// with a single addition site (the fixed-base kernel below), which still fit the instruction cache.
+template <class C>
+struct Inl : C {
+    SBV_DEV static void fmul(uint32_t (&r)[C::N], const uint32_t (&a)[C::N], const uint32_t (&b)[C::N]) { C::fmul_inline(r, a, b); }
+    SBV_DEV static void fsqr(uint32_t (&r)[C::N], const uint32_t (&a)[C::N]) { C::fsqr_inline(r, a); }
+};
+template <class C, bool INL> struct PickArith { using type = C; };
+template <class C> struct PickArith<C, true> { using type = Inl<C>; };
+
 // REG = true: registered keys (sbv_set_keys): the key of item i is kidmap[slot[i]].
 // REG = false: keys grouped on the fly: the key of item i is kidmap[i] (>= 0 for every listed item).
-template <class C, int W, int BLOCK, int MINB, bool REG>
+// One loop over the NWIN windows of u2*Q and then the GWINS windows of u1*G: a single addition site, with the table
+// entry of the next window (a random 64-byte gather) in flight while the current one is added.
+template <class C, int W, int BLOCK, int MINB, bool REG, bool INL>
 __global__ void __launch_bounds__(BLOCK, MINB) k_verify_kt(uint32_t n, const uint32_t *__restrict__ slot, const int32_t *__restrict__ kidmap,
                                                             uint32_t n_slots, const uint8_t *__restrict__ keyflags,
                                                             const uint8_t *__restrict__ r_be, const uint32_t *__restrict__ uw,
                                                             const uint8_t *__restrict__ flags, const uint4 *__restrict__ gtab,
                                                             const uint4 *__restrict__ ktab, uint8_t *__restrict__ ok_out,
                                                             const uint32_t *__restrict__ list, const uint32_t *__restrict__ count) {
+    using A = typename PickArith<C, INL>::type;  // arithmetic policy
     constexpr int N = C::N;
     constexpr int EU4 = 2 * N / 4;  // uint4 per table entry
     using KT = KeyTab<32 * N, W>;
+    constexpr int TOTAL = KT::NWIN + C::GWINS;
     const uint32_t t = blockIdx.x * BLOCK + threadIdx.x;
     if (t >= (list ? __ldg(count) : n)) return;
     const uint32_t idx = list ? __ldg(list + t) : t;
@@ -426,32 +441,39 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_verify_kt(uint32_t n, const uin
     const uint4 *kt = ktab + (size_t)kid * KT::POINTS * EU4;
     uint32_t one[N];
     C::get_one(one);
-    Jac<C> acc;
+    Jac<A> acc;
     mp_copy<N>(acc.X, one);
     mp_copy<N>(acc.Y, one);
 #pragma unroll
     for (int i = 0; i < N; i++) acc.Z[i] = 0;
-    // software pipeline: the table entry of the next window is in flight while the current one is added
-    uint32_t kx[N], ky[N];
-    int d = booth_digit_u2<C, W>(uw, n, idx, 0);
-    {
-        const int e = d < 0 ? -d : d;
-        load_affine<C>(kx, ky, kt + (size_t)(e ? e - 1 : 0) * EU4);
-    }
-#pragma unroll 1
-    for (int win = 0; win < KT::NWIN; win++) {
-        uint32_t nkx[N], nky[N];
-        int nd = 0;
-        if (win + 1 < KT::NWIN) {
-            nd = booth_digit_u2<C, W>(uw, n, idx, win + 1);
-            const int e = nd < 0 ? -nd : nd;
-            load_affine<C>(nkx, nky, kt + ((size_t)(win + 1) * KT::ENT + (e ? e - 1 : 0)) * EU4);
+    // window w < NWIN: signed digit of u2 into the key's table; w >= NWIN: comb digit of u1 into the table of G
+    auto fetch = [&](int w, uint32_t (&x)[N], uint32_t (&y)[N], bool &neg, bool &skip) {
+        if (w < KT::NWIN) {
+            const int d = booth_digit_u2<C, W>(uw, n, idx, w);
+            const int e = d < 0 ? -d : d;
+            load_affine<C>(x, y, kt + ((size_t)w * KT::ENT + (e ? e - 1 : 0)) * EU4);
+            neg = d < 0; skip = d == 0;
+        } else {
+            const int g = w - KT::NWIN;
+            const uint32_t b = comb_digit_u1<C>(uw, n, idx, g);
+            load_affine<C>(x, y, gtab + (((size_t)g << C::GW) + b) * EU4);
+            neg = false; skip = b == 0;
         }
-        pt_add<C, true>(acc, kx, ky, one, d < 0, d == 0);
-        if (win + 1 < KT::NWIN) { mp_copy<N>(kx, nkx); mp_copy<N>(ky, nky); d = nd; }
+    };
+    uint32_t cx[N], cy[N];
+    bool cneg, cskip;
+    fetch(0, cx, cy, cneg, cskip);
+#pragma unroll 1
+    for (int w = 0; w < TOTAL; w++) {
+        uint32_t nx[N], ny[N];
+        bool nneg = false, nskip = true;
+        if (w + 1 < TOTAL) fetch(w + 1, nx, ny, nneg, nskip);
+        pt_add<A, true>(acc, cx, cy, one, cneg, cskip);
+        if (w + 1 < TOTAL) { mp_copy<N>(cx, nx); mp_copy<N>(cy, ny); cneg = nneg; cskip = nskip; }
     }
-    add_u1G<C>(acc, uw, n, idx, gtab);
-    ok_out[idx] = final_check<C>(acc, r_be, idx) ? 1 : 0;
+    Jac<C> fin;
+    mp_copy<N>(fin.X, acc.X); mp_copy<N>(fin.Y, acc.Y); mp_copy<N>(fin.Z, acc.Z);
+    ok_out[idx] = final_check<C>(fin, r_be, idx) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -131,7 +131,9 @@ static __global__ void __launch_bounds__(256) k_kg_route(uint32_t n, const uint3
 
 // nkeys_ptr: device counter (clamped to cap) — the grid is sized for the worst case and surplus threads leave.
 // key k is item keylist[k] of (qx_be, qy_be); for registered keys keylist is the identity over the key array.
-template <class C, int W>
+// INL: the eight multiplications of the doubling inlined (one site, ~25 KB): this kernel is a single dependent chain per
+// thread on an otherwise idle SM sub-partition, so what counts is how well independent multiplications interleave.
+template <class C, int W, bool INL>
 __global__ void __launch_bounds__(64) k_kt_bases(const uint32_t *__restrict__ nkeys_ptr, uint32_t cap, const uint32_t *__restrict__ keylist,
                                                  const uint8_t *__restrict__ qx_be, const uint8_t *__restrict__ qy_be,
                                                  uint32_t *__restrict__ bases, uint8_t *__restrict__ keyflags) {
@@ -142,7 +144,8 @@ __global__ void __launch_bounds__(64) k_kt_bases(const uint32_t *__restrict__ nk
     if (nkeys > cap) nkeys = cap;
     if (k >= nkeys) return;
     const uint32_t item = keylist ? keylist[k] : k;
-    Jac<C> B;
+    using A = typename PickArith<C, INL>::type;
+    Jac<A> B;
     const bool good = load_key<C>(B.X, B.Y, qx_be, qy_be, item);
     keyflags[k] = good ? 1 : 0;
     if (!good) return;  // no table: every item of this key rejects (k_verify_kt checks the flag)
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(64) k_kt_bases(const uint32_t *__restrict__ nk
     for (int win = 0; win < KT::NWIN; win++) {
         if (win) {
 #pragma unroll 1
-            for (int d = 0; d < W; d++) pt_double<C>(B);
+            for (int d = 0; d < W; d++) pt_double<A>(B);
         }
         uint32_t *o = bases + (size_t)win * 3 * N * cap + k;
 #pragma unroll
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(64) k_kt_inv(const uint32_t *__restrict__ nkey
         C::fmul(run, run, z);
     }
     uint32_t inv[N];
-    f_inv<C>(inv, run);
+    p_inv<C>(inv, run);  // binary extended GCD: this thread is alone on its chain, the dependent length is what counts
 #pragma unroll 1
     for (int win = KT::NWIN - 1; win >= 0; win--) {
         uint32_t z[N], pv[N], zi[N];
@@ -299,12 +302,25 @@ __global__ void __launch_bounds__(64) k_kt_final(const uint32_t *__restrict__ nk
         for (int i = 0; i < N; i++) zi[i] = zp[(size_t)i * cap];
     }
     uint32_t *out = ktab + ((size_t)k * KT::NWIN + win) * KT::ENT * 2 * N;
-#pragma unroll 1
-    for (int e = KT::ENT; e >= 1; e--) {
-        uint32_t *oe = out + (size_t)(e - 1) * 2 * N;
-        uint32_t x[N], y[N], z2[N], z3[N];
+    // entry e-1 and its Z ratio are loaded before entry e is converted and stored (independent addresses: the loads
+    // overlap the six multiplications)
+    uint32_t x[N], y[N], h[N];
+    {
+        const uint32_t *oe = out + (size_t)(KT::ENT - 1) * 2 * N;
 #pragma unroll
         for (int i = 0; i < N; i++) { x[i] = oe[i]; y[i] = oe[N + i]; }
+    }
+#pragma unroll 1
+    for (int e = KT::ENT; e >= 1; e--) {
+        uint32_t nx[N], ny[N], nh[N];
+        if (e >= 2) {
+            const uint32_t *on = out + (size_t)(e - 2) * 2 * N;
+            const uint32_t *hp = hs + ((size_t)win * (KT::ENT - 1) + (e - 2)) * N * cap + k;
+#pragma unroll
+            for (int i = 0; i < N; i++) { nx[i] = on[i]; ny[i] = on[N + i]; nh[i] = hp[(size_t)i * cap]; }
+        }
+        uint32_t *oe = out + (size_t)(e - 1) * 2 * N;
+        uint32_t z2[N], z3[N];
         C::fsqr(z2, zi);
         C::fmul(z3, z2, zi);
         C::fmul(x, x, z2);
@@ -312,11 +328,9 @@ __global__ void __launch_bounds__(64) k_kt_final(const uint32_t *__restrict__ nk
 #pragma unroll
         for (int i = 0; i < N; i++) { oe[i] = x[i]; oe[N + i] = y[i]; }
         if (e >= 2) {  // 1/Z_{e-1} = (1/Z_e) * H_e
-            uint32_t h[N];
-            const uint32_t *hp = hs + ((size_t)win * (KT::ENT - 1) + (e - 2)) * N * cap + k;
-#pragma unroll
-            for (int i = 0; i < N; i++) h[i] = hp[(size_t)i * cap];
+            mp_copy<N>(h, nh);
             C::fmul(zi, zi, h);
+            mp_copy<N>(x, nx); mp_copy<N>(y, ny);
         }
     }
     (void)bases;

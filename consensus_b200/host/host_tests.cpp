@@ -10,6 +10,7 @@
 #include <thread>
 
 #include "callsites.hpp"
+#include "marshal.hpp"
 
 using namespace sbft;
 
@@ -66,6 +67,55 @@ static void TestProposalDigestFixtures() {
     Proposal big{Bytes(300, 0xaa), {}, {}, 128};
     Bytes d = big.Der();
     CHECK(d[0] == 0x30 && d[1] == 0x82 && d[2] == 0x01 && d[3] == 0x38);
+}
+
+// tests/golden/digests_and_quorum.txt (the oracle's values; tests/test_golden.py pins the oracle to the same file)
+struct GoldenProposal { Proposal p; const char *digest; };
+static std::vector<GoldenProposal> goldenProposals() {
+    return {
+        {Proposal{{1}, {0}, {8, 1}, 1}, "45c32e94b3c427ee4a3f9b5964d3c5f9c15f3cfa7a28093eae8ca10d151fd892"},
+        {Proposal{{2}, {1}, {3}, 1}, "d7707e2a07e57fdfdd54e73b869e3668f64db840920225cb3cc6bcaf509e45dd"},
+        {Proposal{{}, {}, {}, 0}, "cc67164898e13d2ad50b32e740d8841aef5d0be6daefdf13492405ab087f793f"},
+        {Proposal{Bytes(300, 0xaa), {'h'}, Bytes(130, 'm'), 128}, "99adadae41630b50ef7271ed34dfc1b9683e99a2ea7b2a41b76b337da9bef0ee"},
+        {Proposal{{'p'}, {}, {}, -1}, "df1e849969833046e2920cedcad6355e1416526e8aee58b3d34114899c44e512"},
+        {Proposal{{'p'}, {'q'}, {'r'}, (int64_t)1 << 40}, "ca563970278c698b36ace68926c2b505f7cae38ee36a3694e35909101a6dc562"},
+    };
+}
+static const char *GOLDEN_COMMITSIGS = "ffc4b7e5e35c1ec4fe5cc27aab3f5ab06f2e721d97dd267e793e7c944105483b";
+static std::vector<Signature> goldenCommitSigs() { return {Signature{1, {4}, {5}}, Signature{2, Bytes(70, 4), {}}}; }
+
+static void TestGoldenDigests() {  // types.go:50-69, util.go:564-595 against the oracle's golden values
+    for (auto &g : goldenProposals()) CHECK(g.p.Digest() == g.digest);
+    CHECK(hex(CommitSignaturesDigest(goldenCommitSigs())) == GOLDEN_COMMITSIGS);
+}
+
+static void TestWireCodecs() {  // messages.proto:41-58, 92-96
+    CommitMsg c; c.View = 3; c.Seq = 77; c.Digest = std::string(64, 'a'); c.Sig = ProtoSignature{9, {1, 2, 3}, {4, 5}}; c.Assist = true;
+    Bytes w = MarshalCommit(c);
+    CommitView v;
+    CHECK(DecodeCommit(w.data(), w.size(), v));
+    CHECK(v.View == 3 && v.Seq == 77 && v.Signer == 9 && v.has_sig && v.Assist);
+    CHECK(v.digest_len == 64 && memcmp(v.digest, c.Digest.data(), 64) == 0);
+    CHECK(v.value_len == 3 && v.value[2] == 3 && v.msg_len == 2 && v.msg[1] == 5);
+    // golang/protobuf bytes of Commit{view:1, digest:"ab", signature:{signer:2, value:0x07}}
+    const uint8_t golden[] = {0x08, 0x01, 0x1a, 0x02, 'a', 'b', 0x22, 0x05, 0x08, 0x02, 0x12, 0x01, 0x07};
+    CommitMsg g; g.View = 1; g.Digest = "ab"; g.Sig = ProtoSignature{2, {7}, {}};
+    Bytes gw = MarshalCommit(g);
+    CHECK(gw.size() == sizeof golden && memcmp(gw.data(), golden, sizeof golden) == 0);
+    for (size_t cut = 1; cut < w.size(); cut++) {  // every truncation is either rejected or decodes to a prefix — never reads out of bounds
+        CommitView t;
+        (void)DecodeCommit(w.data(), cut, t);
+    }
+    Bytes bad = w; bad[bad.size() - 3] = 0xff;  // length byte of the last field now overruns
+    CommitView t;
+    (void)DecodeCommit(bad.data(), bad.size(), t);
+    PrepareMsg p{5, 6, "deadbeef", false}, q;
+    Bytes pw = MarshalPrepare(p);
+    CHECK(DecodePrepare(pw.data(), pw.size(), q) && q.View == 5 && q.Seq == 6 && q.Digest == "deadbeef" && !q.Assist);
+    const uint8_t unknown_field[] = {0x08, 0x01, 0x78, 0x05};  // field 15 varint: skipped
+    CHECK(DecodeCommit(unknown_field, sizeof unknown_field, t) && t.View == 1);
+    const uint8_t field_zero[] = {0x00, 0x01};
+    CHECK(!DecodeCommit(field_zero, sizeof field_zero, t));
 }
 
 static void TestQuorum() {  // util_test.go:135-163
@@ -308,6 +358,67 @@ static void TestGpuVerifierEndToEnd() {
     std::vector<Proposal> props = {fixtureProposal(), fixtureWrongProposal(), Proposal{}, Proposal{Bytes(70000, 0x5a), {1, 2, 3}, Bytes(200, 7), -5}, prop, last};
     auto dg = v.DigestBatch(props);
     for (size_t i = 0; i < props.size(); i++) CHECK(dg[i] == props[i].Digest());
+    // ... and both digest kinds equal the ORACLE's golden values, not just the host mirror
+    std::vector<Proposal> gp;
+    for (auto &g : goldenProposals()) gp.push_back(g.p);
+    auto gd = v.DigestBatch(gp);
+    for (size_t i = 0; i < gp.size(); i++) CHECK(gd[i] == goldenProposals()[i].digest);
+    std::vector<Signature> lastSigs;
+    for (auto &ps : vd.LastDecisionSignatures) lastSigs.push_back(Signature{ps.Signer, ps.Value, ps.Msg});
+    std::vector<std::vector<Signature>> sets = {goldenCommitSigs(), std::vector<Signature>(), lastSigs};
+    auto cs = v.CommitSignaturesDigestBatch(sets);
+    CHECK(hex(cs[0]) == GOLDEN_COMMITSIGS && cs[1].empty() && cs[2] == CommitSignaturesDigest(lastSigs));
+
+    // wire Commits -> pinned SoA batch -> one verify + one quorum call (marshal.hpp), against processCommits vote by vote
+    {
+        CommitBatch batch;
+        std::vector<Proposal> props3 = {fixtureProposal(), last, Proposal{{7, 7}, {1}, ViewMetadata{2, 9, 1}.Marshal(), 1}};
+        std::vector<std::vector<Vote>> all_votes;
+        auto slot_of = [&](uint64_t signer) { return signer >= 1 && signer <= 16 ? (int)v.ConsenterSlot(signer) : -1; };
+        v.engine_batch({});  // registry pushed to the engine (sbv_set_keys)
+        for (size_t pi = 0; pi < props3.size(); pi++) {
+            const Proposal &pp = props3[pi];
+            batch.begin_instance(pp.Digest(), 1);
+            std::vector<Vote> vs;
+            for (uint64_t id = 2; id <= 16; id++) {
+                Signature sg = signProposal(id, keys[id], pp, aux);
+                uint64_t sender = id, signer = id;
+                std::string dig = pp.Digest();
+                if (pi == 0 && id == 4) sg.Value[9] ^= 2;                   // bad signature
+                if (pi == 1 && id == 7) dig = fixtureWrongProposal().Digest();  // wrong digest
+                if (pi == 1 && id == 9) signer = 10;                        // signer != sender
+                if (pi == 2 && id == 12) sender = 11;                       // second vote of sender 11
+                if (pi == 2 && id >= 3 && id <= 8) sg.Value[11] ^= 1;       // six bad signatures: quorum fails
+                Vote vt = commitFrom(sender, signer, dig);
+                vt.commit->Sig = ProtoSignature{signer, sg.Value, sg.Msg};
+                vs.push_back(vt);
+                Bytes wire = MarshalCommit(*vt.commit);
+                if (pi == 0 && id == 16) wire.resize(wire.size() - 3);     // truncated on the wire
+                batch.add_wire_commit((uint16_t)sender, wire.data(), wire.size(), slot_of);
+                if (pi == 0 && id == 16) vs.pop_back();                     // the reference never sees an undecodable message
+            }
+            all_votes.push_back(vs);
+        }
+        CHECK(batch.size() == 45 && batch.instances() == 3 && batch.malformed().size() == 1);
+        std::vector<uint8_t> okv2, reached; std::vector<uint32_t> cnt;
+        batch.verify_and_count(v.engine(), q - 1, okv2, cnt, reached);
+        for (size_t pi = 0; pi < props3.size(); pi++) {
+            // reference semantics, vote by vote: how many valid distinct foreign votes does the stream hold?
+            VoteSet set(acceptCommits);
+            int valid = 0;
+            for (auto &vt : all_votes[pi]) {
+                if (vt.sender == 1) continue;
+                size_t before = set.votes().size();
+                set.registerVote(vt.sender, vt);
+                if (set.votes().size() == before) continue;
+                Signature sg{vt.commit->Sig->Signer, vt.commit->Sig->Value, vt.commit->Sig->Msg};
+                if (vt.commit->Digest == props3[pi].Digest() && !v.VerifyConsenterSig(sg, props3[pi]).second) valid++;
+            }
+            CHECK((int)cnt[pi] == valid);
+            CHECK(reached[pi] == (valid >= q - 1 ? 1 : 0));
+        }
+        CHECK(reached[0] == 1 && reached[1] == 1 && reached[2] == 0);
+    }
     for (auto &kv : keys) EC_KEY_free(kv.second.k);
     EC_KEY_free(ck.k);
 }
@@ -315,6 +426,8 @@ static void TestGpuVerifierEndToEnd() {
 int main(int argc, char **argv) {
     std::string mode = argc > 1 ? argv[1] : "cpu";
     RUN(TestProposalDigestFixtures);
+    RUN(TestGoldenDigests);
+    RUN(TestWireCodecs);
     RUN(TestQuorum);
     RUN(TestBadPrepare);
     RUN(TestBadCommit);

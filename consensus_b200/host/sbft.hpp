@@ -121,8 +121,7 @@ struct RequestInfo {  // types.go:41-44
 };
 
 // CommitSignaturesDigest — util.go:564-586; empty input -> empty (nil)
-inline Bytes CommitSignaturesDigest(const std::vector<Signature> &sigs) {
-    if (sigs.empty()) return {};
+inline Bytes CommitSignaturesDer(const std::vector<Signature> &sigs) {  // asn1.Marshal(IntDoubleBytes{A: [...]}) — util.go:570-578
     Bytes inner;
     for (const auto &s : sigs) {
         Bytes one;
@@ -130,7 +129,11 @@ inline Bytes CommitSignaturesDigest(const std::vector<Signature> &sigs) {
         Bytes sq = der::seq(one);
         inner.insert(inner.end(), sq.begin(), sq.end());
     }
-    return sha256(der::seq(der::seq(inner)));
+    return der::seq(der::seq(inner));
+}
+inline Bytes CommitSignaturesDigest(const std::vector<Signature> &sigs) {
+    if (sigs.empty()) return {};
+    return sha256(CommitSignaturesDer(sigs));
 }
 
 // computeQuorum — util.go:183-187 (ceil((n+f+1)/2) == (n+f+2)/2 in integers)

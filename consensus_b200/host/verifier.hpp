@@ -85,6 +85,25 @@ inline bool parse_der_sig(const Bytes &sig, uint8_t r[32], uint8_t s[32]) {
     return rd_int(p, end, r) && rd_int(p, end, s) && p == end;
 }
 
+// ---- pinned host memory from the engine (sbv_host_alloc): what the engine DMAs from without a staging copy ----
+struct PinnedBuf {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    ~PinnedBuf() { if (p) sbv_host_free(p); }
+    void reserve(size_t n, size_t keep = 0) {
+        if (n <= cap) return;
+        size_t nc = std::max(n, cap * 2 + 4096);
+        uint8_t *q = (uint8_t *)sbv_host_alloc(nc);
+        if (!q) throw EngineFault("sbv_host_alloc failed");
+        if (p && keep) memcpy(q, p, keep);
+        if (p) sbv_host_free(p);
+        p = q; cap = nc;
+    }
+};
+
 // One unit of work for the engine: verify (r, s) by key (X||Y) over SHA-256(message).
 struct SigItem {
     uint8_t r[32], s[32];
@@ -229,27 +248,60 @@ class GpuVerifier : public IVerifier {
     void SetConsenterKey(uint64_t id, const uint8_t xy[64]) { std::lock_guard<std::mutex> lk(mu_); consenters_[id] = slot_of(xy); }
     void SetClientKey(const std::string &client, const uint8_t xy[64]) { std::lock_guard<std::mutex> lk(mu_); clients_[client] = slot_of(xy); }
     void SetVerificationSequence(uint64_t v) { std::lock_guard<std::mutex> lk(mu_); verSeq_ = v; }
+    uint32_t ConsenterSlot(uint64_t id) { std::lock_guard<std::mutex> lk(mu_); auto k = consenters_.find(id); return k == consenters_.end() ? 0xffffffffu : k->second; }
     Aggregator &aggregator() { return *agg_; }
     sbv_engine *engine() { return eng_; }
 
     // One engine call: SHA-256 of every message and ECDSA-P256 verification against the registered
     // keys, both on the GPU.
     std::vector<uint8_t> engine_batch(const std::vector<SigItem> &items) {
-        sync_registry();
+        sync_registry();  // also with an empty batch: callers use that to push the registry to the engine
         const size_t n = items.size();
-        std::vector<uint8_t> r(n * 32), s(n * 32), ok(n), msgs;
-        std::vector<uint32_t> slot(n);
-        std::vector<uint64_t> off(n + 1, 0);
+        std::vector<uint8_t> ok(n);
+        if (n == 0) return ok;
+        // flatten straight into pinned memory (one block per calling thread, reused): r | s | slot | off | msgs
+        static thread_local PinnedBuf pin;
+        size_t total = 0;
+        for (const auto &it : items) total += it.message.size();
+        const size_t o_s = 32 * n, o_slot = 64 * n, o_off = o_slot + 4 * n + (8 - (4 * n) % 8) % 8, o_msgs = o_off + 8 * (n + 1);
+        pin.reserve(o_msgs + total + 16);
+        uint8_t *r = pin.p, *s = pin.p + o_s, *msgs = pin.p + o_msgs;
+        uint32_t *slot = (uint32_t *)(pin.p + o_slot);
+        uint64_t *off = (uint64_t *)(pin.p + o_off);
+        size_t pos = 0;
+        off[0] = 0;
         for (size_t i = 0; i < n; i++) {
-            memcpy(&r[32 * i], items[i].r, 32); memcpy(&s[32 * i], items[i].s, 32);
+            memcpy(r + 32 * i, items[i].r, 32); memcpy(s + 32 * i, items[i].s, 32);
             slot[i] = items[i].slot;
-            msgs.insert(msgs.end(), items[i].message.begin(), items[i].message.end());
-            off[i + 1] = msgs.size();
+            if (!items[i].message.empty()) memcpy(msgs + pos, items[i].message.data(), items[i].message.size());
+            pos += items[i].message.size();
+            off[i + 1] = pos;
         }
-        if (msgs.empty()) msgs.push_back(0);
-        int rc = sbv_hash_verify_registered(eng_, SBV_P256, n, msgs.data(), off.data(), slot.data(), r.data(), s.data(), ok.data());
+        int rc = sbv_hash_verify_registered(eng_, SBV_P256, n, msgs, off, slot, r, s, ok.data());
         if (rc != SBV_OK) throw EngineFault(std::string("sbv_hash_verify_registered: ") + sbv_last_error(eng_));
         return ok;
+    }
+
+    // CommitSignaturesDigest for MANY signature sets (internal/bft/util.go:564-595): DER framing on the host, the
+    // SHA-256 chains on the GPU in one call.  An empty set yields an empty digest (nil, util.go:565-567).
+    std::vector<Bytes> CommitSignaturesDigestBatch(const std::vector<std::vector<Signature>> &sets) {
+        std::vector<Bytes> out(sets.size());
+        Bytes blob;
+        std::vector<uint64_t> off{0};
+        std::vector<size_t> where;
+        for (size_t i = 0; i < sets.size(); i++) {
+            if (sets[i].empty()) continue;
+            Bytes d = CommitSignaturesDer(sets[i]);
+            blob.insert(blob.end(), d.begin(), d.end());
+            off.push_back(blob.size());
+            where.push_back(i);
+        }
+        if (where.empty()) return out;
+        Bytes dig(where.size() * 32);
+        if (sbv_sha256_batch(eng_, where.size(), blob.data(), off.data(), dig.data()) != SBV_OK)
+            throw EngineFault(std::string("sbv_sha256_batch: ") + sbv_last_error(eng_));
+        for (size_t k = 0; k < where.size(); k++) out[where[k]] = Bytes(dig.begin() + 32 * k, dig.begin() + 32 * k + 32);
+        return out;
     }
 
     // Proposal.Digest for MANY proposals (pkg/types/types.go:50-69): DER framing on the host, every SHA-256

@@ -175,6 +175,12 @@ int sbv_verify_batch_ranked(sbv_engine *e, int channel, uint8_t curve, size_t n,
                             const uint8_t *qx, const uint8_t *qy, const uint8_t *digest, uint8_t digest_len, uint8_t *ok,
                             uint32_t *mask_all);
 
+/* Pinned (page-locked, portable) host memory for batches the host marshals itself: buffers from here are DMA'd
+ * directly by every entry point (no staging copy).  A cgo shim keeps C memory anyway (cgo pointer rules), so its
+ * batch buffers should come from here.  NULL on failure. */
+void *sbv_host_alloc(size_t bytes);
+void sbv_host_free(void *p);
+
 /* Introspection for benchmarks: number of kernel launches issued by this engine so far. */
 uint64_t sbv_kernel_launches(const sbv_engine *e);
 /* Optional CUDA-event timing inside every verify launch (off by default).  sbv_profile_read sums, over all

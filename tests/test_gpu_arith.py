@@ -72,6 +72,9 @@ def test_field_ops(eng, curve):
     xs = [v for v in _edge_values(c.p, rng, 20) if v]
     got = _run(eng, curve, 4, [(x * R % c.p, 0) for x in xs], [(0, 0)] * len(xs))
     assert [g[0] for g in got] == [pow(x, -1, c.p) * R % c.p for x in xs]
+    xs = [v for v in _edge_values(c.p, rng, 600) if v] + [pow(2, k, c.p) for k in (1, 31, 32, 33, 64, 96, 128, 224, 255, 256, 300)]
+    got = _run(eng, curve, 10, [(x * R % c.p, 0) for x in xs], [(0, 0)] * len(xs))   # binary-GCD field inverse (table construction)
+    assert [g[0] for g in got] == [pow(x, -1, c.p) * R % c.p for x in xs]
     # scalar-field inverse (binary extended GCD): many random values plus powers of two and their
     # neighbours, which exercise long runs of trailing zeros (tz = 31 passes, zero low words)
     xs = [v for v in _edge_values(c.n, rng, 1500) if v]

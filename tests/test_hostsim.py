@@ -80,6 +80,9 @@ def test_field_ops(hs, curve):
     xs = [v for v in _edge_values(c.p, rng, 10) if v]
     got = _run(hs, curve, 4, [(x * R % c.p, 0) for x in xs], [(0, 0)] * len(xs))
     assert [g[0] for g in got] == [pow(x, -1, c.p) * R % c.p for x in xs]
+    xs = [v for v in _edge_values(c.p, rng, 300) if v] + [pow(2, k, c.p) for k in (1, 31, 32, 33, 64, 96, 128, 224, 255, 256, 300)]
+    got = _run(hs, curve, 10, [(x * R % c.p, 0) for x in xs], [(0, 0)] * len(xs))   # binary-GCD field inverse
+    assert [g[0] for g in got] == [pow(x, -1, c.p) * R % c.p for x in xs]
     xs = [v for v in _edge_values(c.n, rng, 200) if v]
     xs += [pow(2, k, c.n) for k in (1, 31, 32, 33, 63, 64, 65, 96, 128, 255, 256, 300, 383)]
     got = _run(hs, curve, 8, [(x * R % c.n, 0) for x in xs], [(0, 0)] * len(xs))

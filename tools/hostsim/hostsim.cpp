@@ -103,12 +103,12 @@ static void verify_grouped_t(uint32_t n, const uint8_t *r, const uint8_t *s, con
     const size_t cap = max_keys ? max_keys : 1;
     std::vector<uint32_t> bases(KS::bases_words(cap)), hs(KS::hs_words(cap)), ztop(KS::ztop_words(cap)), pref(KS::ztop_words(cap)), ktab(KS::ktab_words(cap));
     std::vector<uint8_t> kflags(cap, 0);
-    run_grid((unsigned)((cap + 63) / 64), 64, [&] { k_kt_bases<C, W>(counters.data(), (uint32_t)cap, keylist.data(), qx, qy, bases.data(), kflags.data()); });
+    run_grid((unsigned)((cap + 63) / 64), 64, [&] { k_kt_bases<C, W, true>(counters.data(), (uint32_t)cap, keylist.data(), qx, qy, bases.data(), kflags.data()); });
     run_grid((unsigned)((cap * KT::NWIN + 63) / 64), 64, [&] { k_kt_fill<C, W>(counters.data(), (uint32_t)cap, bases.data(), kflags.data(), hs.data(), ztop.data(), ktab.data()); });
     run_grid((unsigned)((cap + 63) / 64), 64, [&] { k_kt_inv<C, W>(counters.data(), (uint32_t)cap, kflags.data(), ztop.data(), pref.data()); });
     run_grid((unsigned)((cap * KT::NWIN + 63) / 64), 64, [&] { k_kt_final<C, W>(counters.data(), (uint32_t)cap, bases.data(), kflags.data(), hs.data(), ztop.data(), ktab.data()); });
     run_grid((n + 63) / 64, 64, [&] {
-        k_verify_kt<C, W, 64, 1, false>(n, nullptr, item_kid.data(), 0, kflags.data(), r, uw.data(), flags.data(), gtab,
+        k_verify_kt<C, W, 64, 1, false, false>(n, nullptr, item_kid.data(), 0, kflags.data(), r, uw.data(), flags.data(), gtab,
                                         reinterpret_cast<const uint4 *>(ktab.data()), ok, klist.data(), counters.data() + 1);
     });
     run_grid((n + 63) / 64, 64, [&] {

@@ -64,6 +64,51 @@ void run(const char *name, uint32_t *d, int sms) {
     printf("%-28s NW=%2d NA=%2d : %.3f ms  %.1f cyc/warp-iter  -> %.2f cyc per instr (of %d)\n", name, NW, NA, best, per_iter, per_iter / (NW + NA), NW + NA);
 }
 
+// SHFL mixes: what a limb-per-lane layout pays.  NS shuffles per iteration (each moves one 32-bit limb between lanes),
+// optionally beside NW wide MADs.
+template <int NW, int NS>
+__global__ void ks(uint32_t *out, int iters) {
+    uint32_t a = threadIdx.x * 2654435761u + 1, b = blockIdx.x * 40503u + 7;
+    uint32_t w[16], x[8];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = a + i;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = b + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int c = 0; c < NW / 4; c++) {
+            madw(w[0 + (c & 1) * 8], w[1 + (c & 1) * 8], a, b + c);
+            madcw(w[2 + (c & 1) * 8], w[3 + (c & 1) * 8], a, b);
+            madcw(w[4 + (c & 1) * 8], w[5 + (c & 1) * 8], a, b);
+            madcw(w[6 + (c & 1) * 8], w[7 + (c & 1) * 8], a, b);
+        }
+#pragma unroll
+        for (int i = 0; i < NS; i++) x[i & 7] = __shfl_xor_sync(0xffffffffu, x[i & 7] + (uint32_t)i, 1 + (i & 3));
+        a ^= w[3]; b += x[5];
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += w[i];
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= x[i];
+    if (s == 0x12345) out[0] = s;
+}
+template <int NW, int NS>
+void runs(const char *name, uint32_t *d, int sms) {
+    const int iters = 2048, blocks = sms * 4, threads = 512;
+    ks<NW, NS><<<blocks, threads>>>(d, 16);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        cudaEventRecord(e0); ks<NW, NS><<<blocks, threads>>>(d, iters); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
+    }
+    int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
+    double warps_per_smsp = (double)blocks * threads / 32 / (sms * 4);
+    double per_iter = best * 1e-3 * clk * 1e3 / iters / warps_per_smsp;
+    printf("%-28s NW=%2d NS=%2d : %.3f ms  %.1f cyc/warp-iter  (SHFL+its add: %.2f cyc each when NW=0)\n", name, NW, NS, best, per_iter, NS ? per_iter / NS : 0.0);
+}
+
 int main() {
     uint32_t *d; cudaMalloc(&d, 4096);
     cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
@@ -77,5 +122,10 @@ int main() {
     run<32, 64, 0>("mix wide:add 1:2", d, sms);
     run<16, 64, 0>("mix wide:add 1:4", d, sms);
     run<32, 64, 1>("mix plainwide:add 1:2", d, sms);
+    runs<0, 16>("shfl only", d, sms);
+    runs<0, 32>("shfl only", d, sms);
+    runs<32, 0>("wide only (same harness)", d, sms);
+    runs<32, 16>("wide + 16 shfl", d, sms);
+    runs<32, 32>("wide + 32 shfl", d, sms);
     return 0;
 }
