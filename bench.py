@@ -509,7 +509,7 @@ def run_extras(eng, sbv, oracle, np, torch, dev, rank, world, local_rank, mad_pe
     vlo, vhi = int(np.searchsorted(inst, ilo, "left")), (total if rank == world - 1 else int(np.searchsorted(inst, ihi, "left")))
     sl = slice(vlo, vhi)
     F = {k: pin(rep4(tile[k])[sl]) for k in ("r", "s", "qx", "qy", "digest")}
-    cols = [pin(inst[sl]), pin(sender[sl]), pin(signer[sl]), pin(dm[sl]), pin(self_id[ilo:ihi])]
+    cols = [pin(inst[sl] - np.uint32(ilo)), pin(sender[sl]), pin(signer[sl]), pin(dm[sl]), pin(self_id[ilo:ihi])]   # instance ids local to the rank's shard
     nv, ni = vhi - vlo, ihi - ilo
     ok_h, cnt_h, rch_h = pin(np.zeros(nv, np.uint8)), pin(np.zeros(ni, np.uint32)), pin(np.zeros(ni, np.uint8))
     wi = (I // world + 1 + 31) // 32
@@ -523,8 +523,10 @@ def run_extras(eng, sbv, oracle, np, torch, dev, rank, world, local_rank, mad_pe
                                               ctypes.c_size_t(ni), vp(cols[4].data_ptr()), ctypes.c_uint32(10), vp(ok_h.data_ptr()),
                                               vp(cnt_h.data_ptr()), vp(rch_h.data_ptr())), "sbv_verify_quorum")
         if world > 1:   # every rank learns which instances reached quorum: one NCCL all-gather of the packed bits
-            mine = torch.from_numpy(np.resize(np.packbits(rch_h.numpy(), bitorder="little"), wi * 4).view(np.int32).copy())
-            mine[(ni + 31) // 32:] = 0
+            packed = np.zeros(wi * 4, np.uint8)
+            pb = np.packbits(rch_h.numpy(), bitorder="little")
+            packed[:pb.size] = pb
+            mine = torch.from_numpy(packed.view(np.int32).copy())
             d_rch_all[rank * wi:(rank + 1) * wi].copy_(mine, non_blocking=True)
             eng.gather_words_device(0, d_rch_all.data_ptr(), wi, stream=torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()

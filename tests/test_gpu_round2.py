@@ -202,3 +202,49 @@ def test_concurrent_callers_three_lanes(eng):
     for t in ths: t.start()
     for t in ths: t.join()
     assert not errs, errs
+
+
+# ---- single-process multi-device engine (sbv_create with 2 devices): needs a 2-GPU box ----------------------------
+def _two_gpus():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+
+
+def test_multi_device_verify_quorum_shards_by_instance():
+    """sbv_verify_quorum on a 2-device engine: votes sharded by instance, verdict + reached masks in one NCCL all-gather."""
+    _two_gpus()
+    import consensus_b200 as sbv
+    I, NV = 901, 15      # odd instance count: uneven shards
+    b, inst, sender, signer, dm = _vote_stream(I, NV, 71)
+    sig_ok = oracle.verify_batch(P256, b["r"], b["s"], b["qx"], b["qy"], b["digest"])
+    self_id = np.zeros(I, np.uint16)
+    want_cnt, want_reached = ref.count_commit_votes_batch(inst, sender, signer, dm, sig_ok, I, 10, self_id)
+    with sbv.Engine(n_devices=2) as e2:
+        for _ in range(3):
+            ok, cnt, reached = e2.verify_quorum(P256, b["r"], b["s"], b["qx"], b["qy"], b["digest"], inst, sender, signer, dm, I, 10, self_id=self_id)
+            assert np.array_equal(ok, sig_ok)
+            assert np.array_equal(cnt, want_cnt) and np.array_equal(reached, want_reached)
+
+
+def test_multi_device_concurrent_callers():
+    """Two host threads on a 2-device engine: per-lane gather buffers, collectives issued under one order."""
+    _two_gpus()
+    import threading
+    import consensus_b200 as sbv
+    batches = [corpus.make_batch(P256, n=4001 + 777 * i, K=5 + i, seed=80 + i, corrupt_rate=5) for i in range(3)]
+    wants = [oracle.verify_batch(P256, b["r"], b["s"], b["qx"], b["qy"], b["digest"]) for b in batches]
+    errs = []
+    with sbv.Engine(n_devices=2) as e2:
+        def work(i):
+            try:
+                for _ in range(4):
+                    b = batches[i]
+                    if not np.array_equal(e2.verify_batch(P256, b["r"], b["s"], b["qx"], b["qy"], b["digest"]), wants[i]):
+                        errs.append(i)
+            except Exception as ex:
+                errs.append(repr(ex))
+        ths = [threading.Thread(target=work, args=(i,)) for i in range(3)]
+        for t in ths: t.start()
+        for t in ths: t.join()
+    assert not errs, errs
