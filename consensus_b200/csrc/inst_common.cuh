@@ -7,7 +7,10 @@
 namespace sbv {
 
 template <class C> struct Cfg;
-template <> struct Cfg<P256> { static constexpr int COZ_MINB = 7, KT_MINB = 7, KT_VARIANT = 0; };
+// P-256: the fixed-base kernel runs with its multiplications inlined at 6 blocks of 64 threads per SM (163 registers, no
+// spills; profiles/r02_variants.md: equal or slightly ahead of the out-of-line build at 7 blocks, which spills 80 B);
+// the generic kernel likewise at 6 blocks (no spills) now that it only sees the keys that do not repeat.
+template <> struct Cfg<P256> { static constexpr int COZ_MINB = 6, KT_MINB = 7, KT_VARIANT = 2; };
 template <> struct Cfg<P384> { static constexpr int COZ_MINB = 4, KT_MINB = 4, KT_VARIANT = 0; };
 
 template <class C>
@@ -72,6 +75,7 @@ cudaError_t op_kt_verify(int reg, int warp, uint32_t n, const uint32_t *slot, co
         k_verify_kt_warp<C, W><<<(unsigned)(((size_t)n * 32 + 127) / 128), 128, 0, st>>>(n, slot, kidmap, n_slots, keyflags, r, uw, flags, g4, k4, ok);
     } else if (reg) {
         if (variant == 1) k_verify_kt<C, W, BLOCK, MINB, true, true><<<blocks, BLOCK, 0, st>>>(SBV_KT_ARGS);
+        else if (variant == 2) k_verify_kt<C, W, BLOCK, MINB - 1, true, true><<<blocks, BLOCK, 0, st>>>(SBV_KT_ARGS);
         else k_verify_kt<C, W, BLOCK, MINB, true, false><<<blocks, BLOCK, 0, st>>>(SBV_KT_ARGS);
     } else {
         if (variant == 1) k_verify_kt<C, W, BLOCK, MINB, false, true><<<blocks, BLOCK, 0, st>>>(SBV_KT_ARGS);          // multiplications inlined
