@@ -122,6 +122,8 @@ class Aggregator {
         { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
         cv_.notify_all();
         th_.join();
+        std::unique_lock<std::mutex> lk(mu_);
+        idle_cv_.wait(lk, [&] { return inflight_ == 0; });
     }
     // Blocks until the batch this item joined has been verified; returns the item's verdict.
     bool submit(SigItem item) {
@@ -147,16 +149,22 @@ class Aggregator {
         std::optional<std::string> fault;
         std::condition_variable cv;
     };
-    void flush_locked(std::unique_lock<std::mutex> &lk) {
+    // Closes the open batch and runs it on its own thread: neither the deadline thread nor the caller that filled the
+    // batch waits for the engine, so consecutive batches overlap on the engine's lanes.
+    void flush_locked(std::unique_lock<std::mutex> &) {
         auto b = open_;
         if (b->items.empty()) return;
         open_ = std::make_shared<Batch>();
-        lk.unlock();
-        try { b->ok = fn_(b->items); } catch (const std::exception &ex) { b->fault = ex.what(); }
-        lk.lock();
-        batches_++; items_ += b->items.size();
-        b->done = true;
-        b->cv.notify_all();
+        inflight_++;
+        std::thread([this, b] {
+            try { b->ok = fn_(b->items); } catch (const std::exception &ex) { b->fault = ex.what(); }
+            std::lock_guard<std::mutex> lk(mu_);
+            batches_++; items_ += b->items.size();
+            b->done = true;
+            b->cv.notify_all();
+            inflight_--;
+            idle_cv_.notify_all();
+        }).detach();
     }
     void run() {
         std::unique_lock<std::mutex> lk(mu_);
@@ -172,9 +180,10 @@ class Aggregator {
     std::chrono::microseconds window_;
     size_t max_;
     std::mutex mu_;
-    std::condition_variable cv_;
+    std::condition_variable cv_, idle_cv_;
     std::shared_ptr<Batch> open_;
     bool stop_ = false;
+    int inflight_ = 0;
     uint64_t batches_ = 0, items_ = 0;
     std::thread th_;
 };
@@ -248,6 +257,13 @@ class GpuVerifier : public IVerifier {
     void SetConsenterKey(uint64_t id, const uint8_t xy[64]) { std::lock_guard<std::mutex> lk(mu_); consenters_[id] = slot_of(xy); }
     void SetClientKey(const std::string &client, const uint8_t xy[64]) { std::lock_guard<std::mutex> lk(mu_); clients_[client] = slot_of(xy); }
     void SetVerificationSequence(uint64_t v) { std::lock_guard<std::mutex> lk(mu_); verSeq_ = v; }
+    // Keys change only with a reconfiguration (a new verification sequence, dependencies.go:65-66): drop the old
+    // registry before registering the new configuration's keys, so rotated keys do not pile up in HBM.
+    void ResetKeys() {
+        std::lock_guard<std::mutex> lk(mu_);
+        registry_.clear(); slots_.clear(); consenters_.clear(); clients_.clear();
+        dirty_ = true;
+    }
     uint32_t ConsenterSlot(uint64_t id) { std::lock_guard<std::mutex> lk(mu_); auto k = consenters_.find(id); return k == consenters_.end() ? 0xffffffffu : k->second; }
     Aggregator &aggregator() { return *agg_; }
     sbv_engine *engine() { return eng_; }

@@ -47,6 +47,8 @@ type Verifier struct {
 	clients    map[string]uint32
 	dirty      bool
 
+	pool sync.Pool // *pinned: one block of page-locked memory per in-flight batch
+
 	agg *aggregator
 }
 
@@ -61,6 +63,7 @@ func New(devices []int) (*Verifier, error) {
 		return nil, fmt.Errorf("sbv_create failed: %d (there is no CPU fallback)", int(rc))
 	}
 	v := &Verifier{eng: eng, slots: map[[64]byte]uint32{}, consenters: map[uint64]uint32{}, clients: map[string]uint32{}}
+	v.pool.New = func() interface{} { return &pinned{} }
 	v.agg = newAggregator(v.engineBatch, 200*time.Microsecond, 65536)
 	return v, nil
 }
@@ -89,6 +92,19 @@ func (v *Verifier) SetConsenterKey(id uint64, xy [64]byte) { v.mu.Lock(); v.cons
 func (v *Verifier) SetClientKey(c string, xy [64]byte)     { v.mu.Lock(); v.clients[c] = v.slotOf(xy); v.mu.Unlock() }
 func (v *Verifier) SetVerificationSequence(s uint64)        { v.mu.Lock(); v.verSeq = s; v.mu.Unlock() }
 
+// ResetKeys drops every registered key. Keys change only with a reconfiguration, i.e. a new verification
+// sequence (dependencies.go:65-66): the application calls ResetKeys, re-registers the new configuration's keys
+// and bumps the sequence, so rotated keys do not pile up in HBM (264 KiB per key and GPU). Client keys of high
+// cardinality should not be registered at all: sbv_hash_verify_batch takes the key with every item and groups
+// the repeated ones on the device.
+func (v *Verifier) ResetKeys() {
+	v.mu.Lock()
+	v.registry, v.slots = nil, map[[64]byte]uint32{}
+	v.consenters, v.clients = map[uint64]uint32{}, map[string]uint32{}
+	v.dirty = true
+	v.mu.Unlock()
+}
+
 // syncRegistry pushes the key registry to the engine (sbv_set_keys builds one comb table per key).
 func (v *Verifier) syncRegistry() {
 	v.mu.Lock()
@@ -97,6 +113,13 @@ func (v *Verifier) syncRegistry() {
 		return
 	}
 	n := len(v.registry)
+	if n == 0 {
+		if rc := C.sbv_set_keys(v.eng, C.uint64_t(v.verSeq), 0, nil, nil, nil); rc != 0 {
+			v.fault("sbv_set_keys", rc)
+		}
+		v.dirty = false
+		return
+	}
 	ids := make([]C.uint64_t, n)
 	curve := make([]C.uint8_t, n)
 	xy := make([]byte, 96*n)
@@ -111,31 +134,62 @@ func (v *Verifier) syncRegistry() {
 	v.dirty = false
 }
 
+// pinned is one block of page-locked host memory from the engine (sbv_host_alloc): C memory, so cgo may hand it
+// to the engine freely, and the engine DMAs from it without a staging copy.
+type pinned struct {
+	p   unsafe.Pointer
+	cap int
+}
+
+func (b *pinned) reserve(n int) []byte {
+	if n > b.cap {
+		if b.p != nil {
+			C.sbv_host_free(b.p)
+		}
+		b.cap = n + n/2 + 4096
+		b.p = C.sbv_host_alloc(C.size_t(b.cap))
+		if b.p == nil {
+			panic("sbv: sbv_host_alloc failed")
+		}
+	}
+	return unsafe.Slice((*byte)(b.p), b.cap)[:n]
+}
+
 // engineBatch is the one cgo crossing: SHA-256 of every message and ECDSA verification against the
-// registered keys, both on the GPU. Go memory is only read during the call (cgo pointer rules).
+// registered keys, both on the GPU. The batch is marshalled straight into pinned memory (one block per
+// in-flight batch, pooled): r | s | slot | off | msgs.
 func (v *Verifier) engineBatch(items []item) []byte {
 	v.syncRegistry()
 	n := len(items)
-	r := make([]byte, 32*n)
-	s := make([]byte, 32*n)
-	slot := make([]uint32, n)
-	off := make([]uint64, n+1)
-	var msgs []byte
-	for i := range items {
-		copy(r[32*i:], items[i].r[:])
-		copy(s[32*i:], items[i].s[:])
-		slot[i] = items[i].slot
-		msgs = append(msgs, items[i].msg...)
-		off[i+1] = uint64(len(msgs))
-	}
-	if len(msgs) == 0 {
-		msgs = []byte{0}
-	}
 	ok := make([]byte, n)
+	if n == 0 {
+		return ok
+	}
+	total := 0
+	for i := range items {
+		total += len(items[i].msg)
+	}
+	oS, oSlot := 32*n, 64*n
+	oOff := (oSlot + 4*n + 7) &^ 7
+	oMsgs := oOff + 8*(n+1)
+	pb := v.pool.Get().(*pinned)
+	defer v.pool.Put(pb)
+	buf := pb.reserve(oMsgs + total + 16)
+	pos := 0
+	binary.LittleEndian.PutUint64(buf[oOff:], 0)
+	for i := range items {
+		copy(buf[32*i:], items[i].r[:])
+		copy(buf[oS+32*i:], items[i].s[:])
+		binary.LittleEndian.PutUint32(buf[oSlot+4*i:], items[i].slot)
+		copy(buf[oMsgs+pos:], items[i].msg)
+		pos += len(items[i].msg)
+		binary.LittleEndian.PutUint64(buf[oOff+8*(i+1):], uint64(pos))
+	}
+	base := uintptr(pb.p)
 	rc := C.sbv_hash_verify_registered(v.eng, C.SBV_P256, C.size_t(n),
-		(*C.uint8_t)(unsafe.Pointer(&msgs[0])), (*C.uint64_t)(unsafe.Pointer(&off[0])),
-		(*C.uint32_t)(unsafe.Pointer(&slot[0])), (*C.uint8_t)(unsafe.Pointer(&r[0])),
-		(*C.uint8_t)(unsafe.Pointer(&s[0])), (*C.uint8_t)(unsafe.Pointer(&ok[0])))
+		(*C.uint8_t)(unsafe.Pointer(base+uintptr(oMsgs))), (*C.uint64_t)(unsafe.Pointer(base+uintptr(oOff))),
+		(*C.uint32_t)(unsafe.Pointer(base+uintptr(oSlot))), (*C.uint8_t)(unsafe.Pointer(base)),
+		(*C.uint8_t)(unsafe.Pointer(base+uintptr(oS))), (*C.uint8_t)(unsafe.Pointer(&ok[0])))
 	if rc != 0 {
 		v.fault("sbv_hash_verify_registered", rc)
 	}
@@ -410,16 +464,18 @@ func newAggregator(fn func([]item) []byte, window time.Duration, max int) *aggre
 	return a
 }
 
+// flushLocked closes the open batch and hands it to its own goroutine: the ticker goroutine and the caller that
+// filled the batch never wait for the engine, so consecutive batches overlap on the engine's lanes.
 func (a *aggregator) flushLocked() {
 	b := a.open
 	if len(b.items) == 0 {
 		return
 	}
 	a.open = &batch{done: make(chan struct{})}
-	a.mu.Unlock()
-	b.ok = a.fn(b.items) // an engine fault panics here: never a verdict
-	close(b.done)
-	a.mu.Lock()
+	go func() {
+		b.ok = a.fn(b.items) // an engine fault panics here: never a verdict
+		close(b.done)
+	}()
 }
 
 // submit blocks until the batch the item joined has been verified (size cap or deadline, whichever is
