@@ -199,6 +199,8 @@ static __device__ __noinline__ Fe8 p256_nmul_call(Fe8 a, Fe8 b) {
 // P-384: generic word-serial Montgomery for both fields (12 limbs).
 // -------------------------------------------------------------------------------------------------
 struct Fe12 { uint32_t v[12]; };
+struct Fe24 { uint32_t v[24]; };
+static __device__ __noinline__ Fe12 p384_redc_call(Fe24 t);
 static __device__ __noinline__ Fe12 p384_fmul_call(Fe12 a, Fe12 b);
 static __device__ __noinline__ Fe12 p384_fsqr_call(Fe12 a);
 static __device__ __noinline__ Fe12 p384_nmul_call(Fe12 a, Fe12 b);
@@ -226,58 +228,65 @@ struct P384 {
     SBV_DEV static uint32_t p_minus_2_limb(int i) { const uint32_t c[12] = SBV_P384_P_MINUS_2; return c[i]; }
     SBV_DEV static uint32_t n_minus_2_limb(int i) { const uint32_t c[12] = SBV_P384_N_MINUS_2; return c[i]; }
 
-    // p = 2^384 - 2^128 - 2^96 + 2^32 - 1 and -p^-1 mod 2^64 = 2^32 + 1, so the quotient digit of a
-    // 64-bit Montgomery step is (t0, t0 + t1) and q*p = q*2^384 - q*2^128 - q*2^96 + q*2^32 - q is shifted
-    // adds: no multiplications in the reduction (one add chain, two subtract chains per step).
+    // p = 2^384 - 2^128 - 2^96 + 2^32 - 1 and -p^-1 = 1 mod 2^32.  U = T + M*p must vanish mod 2^384; with
+    //   V = T + M*2^32 - M*2^96 - M*2^128,   U = V - M + M*2^384
+    // that is M = V mod 2^384: limb k of M is limb k of V, which only involves limbs k-1, k-3, k-4 of M.  So the low half is
+    // one pass over the limbs with a signed carry (each limb: T_k + m_{k-1} - m_{k-3} - m_{k-4} + carry — ptxas turns the
+    // 64-bit sums into 3-input IADD3 with two carry predicates, ~5 instructions per limb), and the result is
+    // floor(V / 2^384) + M, a second pass of the same shape.  No multiplications, ~130 instructions (the digit-serial form,
+    // six 64-bit steps each rippling three chains to the top limb, took ~370).
     SBV_DEV static void redc(uint32_t (&r)[12], uint32_t (&T)[24]) {
-        uint32_t t24 = 0;
+        uint32_t m[12], hi[12];
+        int64_t c = 0;
+        m[0] = T[0];
 #pragma unroll
-        for (int k = 0; k < 6; k++) {
-            const int b = 2 * k;
-            const uint32_t mlo = T[b], mhi = T[b] + T[b + 1];
-            // + q*2^32 and + q*2^384
-            T[b + 1] = add_cc(T[b + 1], mlo);
-            T[b + 2] = addc_cc(T[b + 2], mhi);
-#pragma unroll
-            for (int j = b + 3; j < b + 12; j++) T[j] = addc_cc(T[j], 0);
-            T[b + 12] = addc_cc(T[b + 12], mlo);
-            T[b + 13] = addc_cc(T[b + 13], mhi);
-#pragma unroll
-            for (int j = b + 14; j < 24; j++) T[j] = addc_cc(T[j], 0);
-            t24 = addc(t24, 0);
-            // - q and - q*2^96
-            T[b] = sub_cc(T[b], mlo);
-            T[b + 1] = subc_cc(T[b + 1], mhi);
-            T[b + 2] = subc_cc(T[b + 2], 0);
-            T[b + 3] = subc_cc(T[b + 3], mlo);
-            T[b + 4] = subc_cc(T[b + 4], mhi);
-#pragma unroll
-            for (int j = b + 5; j < 24; j++) T[j] = subc_cc(T[j], 0);
-            t24 = subc(t24, 0);
-            // - q*2^128
-            T[b + 4] = sub_cc(T[b + 4], mlo);
-            T[b + 5] = subc_cc(T[b + 5], mhi);
-#pragma unroll
-            for (int j = b + 6; j < 24; j++) T[j] = subc_cc(T[j], 0);
-            t24 = subc(t24, 0);
+        for (int k = 1; k < 12; k++) {
+            int64_t acc = c + (int64_t)(uint64_t)T[k] + (int64_t)(uint64_t)m[k - 1];
+            if (k >= 3) acc -= (int64_t)(uint64_t)m[k - 3];
+            if (k >= 4) acc -= (int64_t)(uint64_t)m[k - 4];
+            m[k] = (uint32_t)acc;
+            c = acc >> 32;
         }
-        uint32_t hi[12], t[12];
 #pragma unroll
-        for (int i = 0; i < 12; i++) hi[i] = T[12 + i];
-        const uint32_t p[12] = SBV_P384_P;
-        uint32_t bw = mp_sub<12>(t, hi, p);
-        bool use_t = (t24 != 0) || (bw == 0);
-        mp_select<12>(r, use_t, t, hi);
+        for (int i = 0; i < 12; i++) {
+            int64_t acc = c + (int64_t)(uint64_t)T[12 + i] + (int64_t)(uint64_t)m[i];
+            if (i == 0) acc += (int64_t)(uint64_t)m[11];        // top limb of M*2^32
+            if (i < 3) acc -= (int64_t)(uint64_t)m[9 + i];       // top limbs of M*2^96
+            if (i < 4) acc -= (int64_t)(uint64_t)m[8 + i];       // top limbs of M*2^128
+            hi[i] = (uint32_t)acc;
+            c = acc >> 32;
+        }
+        const uint32_t t24 = (uint32_t)c;  // 0 or 1: the result is < 2p
+        // subtract p iff the result is >= p: hi + delta carries out exactly then, delta = 2^384 - p = (1, F, F, 0, 1, 0, ...)
+        uint32_t d[12];
+        d[0] = add_cc(hi[0], 1u);
+        d[1] = addc_cc(hi[1], 0xffffffffu);
+        d[2] = addc_cc(hi[2], 0xffffffffu);
+        d[3] = addc_cc(hi[3], 0u);
+        d[4] = addc_cc(hi[4], 1u);
+#pragma unroll
+        for (int i = 5; i < 12; i++) d[i] = addc_cc(hi[i], 0u);
+        const uint32_t take = addc(t24, 0u);
+#pragma unroll
+        for (int i = 0; i < 12; i++) r[i] = take ? d[i] : hi[i];
+    }
+    // The reduction is kept out of line behind the product: scheduled into the product's twelve carry chains, its
+    // two-predicate additions overflow the predicate file and ptxas spills predicates through LOP3/P2R (+400 instructions).
+    SBV_DEV static void redc_ool(uint32_t (&r)[12], const uint32_t (&T)[24]) {
+        Fe24 t;
+        mp_copy<24>(t.v, T);
+        Fe12 z = p384_redc_call(t);
+        mp_copy<12>(r, z.v);
     }
     SBV_DEV static void fmul_inline(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
         uint32_t T[24];
         mp_mul<12>(T, a, b);
-        redc(r, T);
+        redc_ool(r, T);
     }
     SBV_DEV static void fsqr_inline(uint32_t (&r)[12], const uint32_t (&a)[12]) {
         uint32_t T[24];
         mp_sqr<12>(T, a);
-        redc(r, T);
+        redc_ool(r, T);
     }
     // out of line, operands in registers — same reason as P256::fmul
     SBV_DEV static void fmul(uint32_t (&r)[12], const uint32_t (&a)[12], const uint32_t (&b)[12]) {
@@ -325,6 +334,11 @@ struct P384 {
     }
 };
 
+static __device__ __noinline__ Fe12 p384_redc_call(Fe24 t) {
+    Fe12 r;
+    P384::redc(r.v, t.v);
+    return r;
+}
 static __device__ __noinline__ Fe12 p384_fmul_call(Fe12 a, Fe12 b) {
     Fe12 r;
     P384::fmul_inline(r.v, a.v, b.v);
