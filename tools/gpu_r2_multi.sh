@@ -4,9 +4,9 @@ N=${1:-2}
 STEPS=${2:-20}
 mkdir -p gpurun_out
 nvidia-smi -L | head -8
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -q -k "multi_device" 2>&1 | tail -4
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps $STEPS --warmup 5 > gpurun_out/m_bench_n$N.json 2> gpurun_out/m_bench_n$N.err; tail -5 gpurun_out/m_bench_n$N.err; cut -c1-300 gpurun_out/m_bench_n$N.json
-timeout 600 python bench.py --gpus 1 --steps $STEPS --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/m_bench_n1_of$N.json 2>/dev/null
+timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -q -k "multi_device" 2>&1 | tail -4
+timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps $STEPS --warmup 5 > gpurun_out/m_bench_n$N.json 2> gpurun_out/m_bench_n$N.err; tail -5 gpurun_out/m_bench_n$N.err; cut -c1-300 gpurun_out/m_bench_n$N.json
+timeout 240 python bench.py --gpus 1 --steps $STEPS --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/m_bench_n1_of$N.json 2>/dev/null
 python - <<PY
 import json
 last=lambda f: json.loads([l for l in open(f) if l.startswith("{")][-1])
