@@ -475,7 +475,7 @@ def run_extras(eng, sbv, oracle, np, torch, dev, rank, world, local_rank, mad_pe
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
 
     def best_of(fn, reps=3):
-        for _ in range(4):      # one warm-up call per scratch set of the engine (each grows its buffers on first use)
+        for _ in range(5):      # one warm-up call per scratch set of the engine (each grows its buffers on first use)
             fn()
         best = 1e30
         for _ in range(reps):

@@ -309,7 +309,8 @@ int sync_lane(sbv_engine *e, int lane) {
     return 0;
 }
 
-// stages the five field arrays of items [lo, lo+cnt) on device d's lane and enqueues the verify pipeline
+// stages the five field arrays of items [lo, lo+cnt) on device d's lane and enqueues the verify pipeline: the KEYS go
+// first, so that the grouping and the table construction run while r, s and the digests are still being copied
 int stage_and_verify(sbv_engine *e, Dev &d, int lane, uint8_t curve, size_t lo, size_t cnt, const uint8_t *r, const uint8_t *s, const uint8_t *qx,
                      const uint8_t *qy, const uint8_t *digest, uint8_t digest_len) {
     const size_t L = fbytes(curve);
@@ -318,13 +319,22 @@ int stage_and_verify(sbv_engine *e, Dev &d, int lane, uint8_t curve, size_t lo, 
     int rc = sbv_lane_ensure(e, d, ln, cnt, cnt * (4 * L + digest_len + 1) + 8 * 256);
     if (rc) return rc;
     size_t so = 0;
-    if ((rc = sbv_lane_h2d(e, ln, ln.d_r, r + lo * L, cnt * L, so))) return rc;
-    if ((rc = sbv_lane_h2d(e, ln, ln.d_s, s + lo * L, cnt * L, so))) return rc;
-    if ((rc = sbv_lane_h2d(e, ln, ln.d_dig, digest + lo * digest_len, cnt * digest_len, so))) return rc;
     if ((rc = sbv_lane_h2d(e, ln, ln.d_qx, qx + lo * L, cnt * L, so))) return rc;
     if ((rc = sbv_lane_h2d(e, ln, ln.d_qy, qy + lo * L, cnt * L, so))) return rc;
+    VerifyLaunch vl;
+    {
+        std::lock_guard<std::mutex> lk(e->mu);
+        if ((rc = sbv_launch_verify_begin(e, d, curve, cnt, ln.d_qx, ln.d_qy, ln.stream, &vl))) return rc;
+    }
+    rc = sbv_lane_h2d(e, ln, ln.d_r, r + lo * L, cnt * L, so);
+    if (!rc) rc = sbv_lane_h2d(e, ln, ln.d_s, s + lo * L, cnt * L, so);
+    if (!rc) rc = sbv_lane_h2d(e, ln, ln.d_dig, digest + lo * digest_len, cnt * digest_len, so);
     std::lock_guard<std::mutex> lk(e->mu);
-    return sbv_launch_verify(e, d, curve, cnt, ln.d_r, ln.d_s, ln.d_qx, ln.d_qy, ln.d_dig, digest_len, ln.d_ok, ln.stream);
+    if (rc) {  // a fault between the halves: hand the scratch set back (the caller fail-stops anyway)
+        if (vl.w) vl.w->open = false;
+        return rc;
+    }
+    return sbv_launch_verify_finish(e, d, vl, ln.d_r, ln.d_s, ln.d_dig, digest_len, ln.d_ok, ln.stream);
 }
 
 }  // namespace
@@ -341,6 +351,7 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
     e->keyed_warp_limit = env_int("SBV_KEYED_WARP_LIMIT", 2048);
     e->group_threshold = env_int("SBV_GROUP_THRESHOLD", 16);
     e->group_max_keys = env_int("SBV_GROUP_MAX_KEYS", 8192);
+    e->group_min_batch = env_int("SBV_GROUP_MIN_BATCH", 0);
     {
         // per-engine hash seed: an adversary who picks the keys of a batch cannot aim at the probe sequence
         uint64_t t = (uint64_t)(uintptr_t)e;

@@ -15,7 +15,7 @@
 #include "ops.h"
 
 constexpr int SBV_LANES = 3;    // concurrent host-buffer calls per engine
-constexpr int SBV_SCRATCH = 4;  // verify launches in flight per device
+constexpr int SBV_SCRATCH = 5;  // scratch sets per device (> SBV_LANES + 1: a launch may be held open per lane)
 
 struct Dev {
     int ordinal = 0;
@@ -40,6 +40,7 @@ struct Dev {
         cudaStream_t s_tab = nullptr, s_gen = nullptr;  // table construction / generic kernel run beside the main stream
         cudaEvent_t done = nullptr, ev_group = nullptr, ev_prep = nullptr, ev_tab = nullptr, ev_gen = nullptr;
         bool used = false;
+        bool open = false;  // taken by a launch whose second half has not been enqueued yet
         struct Caps {  // bytes allocated per buffer
             size_t uw = 0, flags = 0, tscr = 0, htab = 0, rep = 0, keylist = 0, klist = 0, glist = 0, zeroed = 0, keyid = 0, item_kid = 0, bases = 0,
                    hs = 0, ztop = 0, pref = 0, ktab = 0, keyflags = 0;
@@ -90,6 +91,7 @@ struct sbv_engine {
     int keyed_warp_limit = 2048;   // registered-key batches up to this size use one warp per signature (SBV_KEYED_WARP_LIMIT)
     int group_threshold = 16;      // a key gets a table when it occurs at least this often in a batch (SBV_GROUP_THRESHOLD; 0 = never)
     int group_max_keys = 8192;     // table slots per launch (SBV_GROUP_MAX_KEYS)
+    int group_min_batch = 0;       // launches smaller than this skip the grouping (SBV_GROUP_MIN_BATCH)
     uint32_t hash_seed = 0x9e3779b9u;
     bool profiling = false;
     // NCCL (loaded lazily with dlopen so single-device, single-rank users never touch it)
@@ -128,10 +130,23 @@ inline int sbv_fail(sbv_engine *e, int code, const char *fmt, ...) {
                             __FILE__, __LINE__);                                                      \
     } while (0)
 
+// one keys-per-item launch between its two halves (pipeline.cu)
+struct VerifyLaunch {
+    Dev::Scratch *w = nullptr;
+    cudaEvent_t *ev = nullptr;
+    const uint8_t *d_qx = nullptr, *d_qy = nullptr;
+    size_t n = 0;
+    uint8_t curve = 0;
+    bool grouping = false;
+};
+
 // ---- pipeline.cu: the verify pipelines (device pointers in, verdict bytes out; enqueue only, no sync) ----
 // keys-per-item: k_prep, key grouping, per-key tables for repeated keys, fixed-base kernel + generic kernel for the rest
 int sbv_launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                       const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
+int sbv_launch_verify_begin(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_qx, const uint8_t *d_qy, cudaStream_t st, VerifyLaunch *vl);
+int sbv_launch_verify_finish(sbv_engine *e, Dev &d, const VerifyLaunch &vl, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_dig, uint32_t dlen,
+                             uint8_t *d_ok, cudaStream_t st);
 // registered keys (sbv_set_keys)
 int sbv_launch_keyed(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint32_t *d_slot, const uint8_t *d_r, const uint8_t *d_s,
                      const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);

@@ -17,7 +17,11 @@ namespace {
 // Takes the next scratch set of device d for a launch on stream st: waits (on the stream) for the set's previous user
 // and grows the buffers to n items / kcap keys of curve `ops` (growth drains the previous user on the host first).
 int take_scratch(sbv_engine *e, Dev &d, const CurveOps &ops, const KtOps *kt, size_t n, size_t kcap, cudaStream_t st, Dev::Scratch **out) {
-    const int idx = (int)(d.ws_next++ % SBV_SCRATCH);
+    // round robin over the sets that are not held open between the two halves of a host-buffer launch (at most
+    // SBV_LANES < SBV_SCRATCH of them at any time)
+    int idx = (int)(d.ws_next++ % SBV_SCRATCH);
+    for (int tries = 0; tries < SBV_SCRATCH && d.ws[idx].open; tries++) idx = (int)(d.ws_next++ % SBV_SCRATCH);
+    if (d.ws[idx].open) return sbv_fail(e, SBV_ERR_ARG, "no free scratch set (more launches held open than lanes?)");
     Dev::Scratch &w = d.ws[idx];
     Dev::Scratch::Caps &c = w.caps;
     if (!w.done) {
@@ -118,14 +122,19 @@ int sbv_init_gtables(sbv_engine *e, Dev &d) {
     return 0;
 }
 
-int sbv_launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
-                      const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st) {
+// The keys-per-item pipeline in two halves, so that a host-buffer call can upload the keys first and let the grouping
+// and the table construction (the latency-bound part) run while the rest of the batch is still on its way:
+//   begin : scratch set, key grouping on st, table construction on the set's side stream   (needs qx, qy)
+//   finish: k_prep, generic kernel on the second side stream, fixed-base kernel, join       (needs r, s, digest)
+int sbv_launch_verify_begin(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_qx, const uint8_t *d_qy, cudaStream_t st,
+                            VerifyLaunch *vl) {
+    *vl = VerifyLaunch{};
     if (n == 0) return 0;
     const CurveOps &ops = sbv_ops(curve);
     const KtOps *kt = ops.kt5;
     const uint32_t nn = (uint32_t)n;
     const uint32_t T = e->group_threshold > 0 ? (uint32_t)e->group_threshold : 0;
-    const bool grouping = T > 0 && n >= T && e->group_max_keys > 0;
+    const bool grouping = T > 0 && n >= T && n >= (size_t)e->group_min_batch && e->group_max_keys > 0;
     size_t kcap = 0;
     if (grouping) {
         kcap = n / T;
@@ -134,18 +143,11 @@ int sbv_launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint
     }
     Dev::Scratch *w = nullptr;
     if (int rc = take_scratch(e, d, ops, grouping ? kt : nullptr, n, kcap, st, &w)) return rc;
-    cudaEvent_t *ev = prof_take(e, d);
-    if (ev) CU(e, cudaEventRecord(ev[0], st));
-    const uint32_t *gtab = d.gtab[curve];
-    if (!grouping) {
-        CU(e, ops.prep(nn, d_r, d_s, d_dig, dlen, w->uw, w->flags, st));
-        if (ev) { CU(e, cudaEventRecord(ev[1], st)); CU(e, cudaEventRecord(ev[2], st)); }
-        CU(e, ops.coz(nn, d_qx, d_qy, d_r, w->uw, w->flags, gtab, w->tscr, d_ok, nullptr, nullptr, st));
-        if (ev) CU(e, cudaEventRecord(ev[3], st));
-        CU(e, cudaEventRecord(w->done, st));
-        e->launches += 2;
-        return 0;
-    }
+    w->open = true;  // until sbv_launch_verify_finish records the set's `done` event
+    vl->w = w; vl->curve = curve; vl->n = n; vl->grouping = grouping; vl->d_qx = d_qx; vl->d_qy = d_qy;
+    vl->ev = prof_take(e, d);
+    if (vl->ev) CU(e, cudaEventRecord(vl->ev[0], st));
+    if (!grouping) return 0;
     uint32_t *counters = w->zeroed, *kcnt = w->zeroed + 4;
     CU(e, cudaMemsetAsync(w->htab, 0xff, (size_t)w->hsize * 4, st));
     CU(e, cudaMemsetAsync(w->zeroed, 0, (n + 4) * 4, st));
@@ -155,11 +157,34 @@ int sbv_launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint
     CU(e, cudaStreamWaitEvent(w->s_tab, w->ev_group, 0));
     CU(e, kt->build(counters + 0, (uint32_t)kcap, w->keylist, d_qx, d_qy, w->bases, w->hs, w->ztop, w->pref, w->ktab, w->keyflags, w->s_tab));
     CU(e, cudaEventRecord(w->ev_tab, w->s_tab));
+    e->launches += 7;
+    return 0;
+}
+
+int sbv_launch_verify_finish(sbv_engine *e, Dev &d, const VerifyLaunch &vl, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_dig,
+                             uint32_t dlen, uint8_t *d_ok, cudaStream_t st) {
+    if (vl.n == 0) return 0;
+    const CurveOps &ops = sbv_ops(vl.curve);
+    const KtOps *kt = ops.kt5;
+    Dev::Scratch *w = vl.w;
+    cudaEvent_t *ev = vl.ev;
+    const uint32_t nn = (uint32_t)vl.n;
+    const uint32_t *gtab = d.gtab[vl.curve];
     CU(e, ops.prep(nn, d_r, d_s, d_dig, dlen, w->uw, w->flags, st));
+    if (!vl.grouping) {
+        if (ev) { CU(e, cudaEventRecord(ev[1], st)); CU(e, cudaEventRecord(ev[2], st)); }
+        CU(e, ops.coz(nn, vl.d_qx, vl.d_qy, d_r, w->uw, w->flags, gtab, w->tscr, d_ok, nullptr, nullptr, st));
+        if (ev) CU(e, cudaEventRecord(ev[3], st));
+        CU(e, cudaEventRecord(w->done, st));
+        w->open = false;
+        e->launches += 2;
+        return 0;
+    }
+    uint32_t *counters = w->zeroed;
     CU(e, cudaEventRecord(w->ev_prep, st));
     if (ev) CU(e, cudaEventRecord(ev[1], st));
     CU(e, cudaStreamWaitEvent(w->s_gen, w->ev_prep, 0));
-    CU(e, ops.coz(nn, d_qx, d_qy, d_r, w->uw, w->flags, gtab, w->tscr, d_ok, w->glist, counters + 2, w->s_gen));
+    CU(e, ops.coz(nn, vl.d_qx, vl.d_qy, d_r, w->uw, w->flags, gtab, w->tscr, d_ok, w->glist, counters + 2, w->s_gen));
     CU(e, cudaEventRecord(w->ev_gen, w->s_gen));
     CU(e, cudaStreamWaitEvent(st, w->ev_tab, 0));
     if (ev) CU(e, cudaEventRecord(ev[2], st));
@@ -167,8 +192,16 @@ int sbv_launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint
     if (ev) CU(e, cudaEventRecord(ev[3], st));
     CU(e, cudaStreamWaitEvent(st, w->ev_gen, 0));
     CU(e, cudaEventRecord(w->done, st));
-    e->launches += 10;
+    w->open = false;
+    e->launches += 3;
     return 0;
+}
+
+int sbv_launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
+                      const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st) {
+    VerifyLaunch vl;
+    if (int rc = sbv_launch_verify_begin(e, d, curve, n, d_qx, d_qy, st, &vl)) return rc;
+    return sbv_launch_verify_finish(e, d, vl, d_r, d_s, d_dig, dlen, d_ok, st);
 }
 
 // ---- registered keys ----------------------------------------------------------------------------------------
