@@ -8,8 +8,10 @@
 //   3 followers          view.go:553-604         VerifyProposal (B requests) + verifyPrevCommitSignatures (Q sigs)
 //   4 nodes              view.go:519-551         processCommits over the N-1 foreign commit votes
 // All four nodes share ONE verifier instance (one GPU); a deployment has one per node, so the GPU
-// figure is a lower bound.  Signatures are produced up front (signing is api.Signer's job).
+// figure is a lower bound.  The nodes of a phase run on their own threads, as the processes of a deployment would.  Signatures are produced up front (signing is api.Signer's job).
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 
@@ -26,16 +28,30 @@ static double run(IVerifier &v, const std::vector<Decision> &ds, int N, int Q, s
         // leader ingress: every request is verified, then pooled (HandleRequest; batched at the pool boundary)
         auto in = v.VerifyRequestBatch(d.reqs);
         for (auto &p : in) if (p.second) allDecided = false;
-        for (uint64_t node = 2; node <= (uint64_t)N; node++) {  // followers: pre-prepare verification
-            auto vp = v.VerifyProposal(d.prop);
-            if (vp.second) allDecided = false;
-            if (prev) { auto pc = verifyPrevCommitSignatures(v, prev->quorumSigs, prev->prop, 1); if (pc.second) allDecided = false; }
+        // the nodes of a deployment run concurrently (one process each): followers verify the pre-prepare in
+        // parallel, then every node collects its commit votes in parallel; a phase ends when its slowest node does
+        std::atomic<bool> good{true};
+        {
+            std::vector<std::thread> th;
+            for (uint64_t node = 2; node <= (uint64_t)N; node++)
+                th.emplace_back([&] {
+                    auto vp = v.VerifyProposal(d.prop);
+                    if (vp.second) good = false;
+                    if (prev) { auto pc = verifyPrevCommitSignatures(v, prev->quorumSigs, prev->prop, 1); if (pc.second) good = false; }
+                });
+            for (auto &t : th) t.join();
         }
-        for (uint64_t node = 1; node <= (uint64_t)N; node++) {  // every node: prepares, then commit votes
-            auto ids = processPrepares(d.prop, Q, node, d.prepares);
-            auto sigs = processCommits(v, d.prop, Q, node, d.commits);
-            if ((int)ids.size() != Q - 1 || (int)sigs.size() != Q - 1) allDecided = false;
+        {
+            std::vector<std::thread> th;
+            for (uint64_t node = 1; node <= (uint64_t)N; node++)
+                th.emplace_back([&, node] {
+                    auto ids = processPrepares(d.prop, Q, node, d.prepares);
+                    auto sigs = processCommits(v, d.prop, Q, node, d.commits);
+                    if ((int)ids.size() != Q - 1 || (int)sigs.size() != Q - 1) good = false;
+                });
+            for (auto &t : th) t.join();
         }
+        if (!good) allDecided = false;
         txs += d.reqs.size();
         prev = &d;
     }
