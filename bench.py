@@ -507,12 +507,12 @@ def run_extras(eng, sbv, oracle, np, torch, dev, rank, world, local_rank, mad_pe
     ok_all = rep4(want_tile)
     self_id = np.zeros(I, np.uint16)                      # node 0 counts the votes of nodes 1..15
     want_cnt, want_reached = ref.count_commit_votes_batch(inst, sender, signer, dm, ok_all, I, 10, self_id)
-    # shard by instance over the ranks
-    ilo, ihi = I * rank // world, I * (rank + 1) // world
-    vlo, vhi = int(np.searchsorted(inst, ilo, "left")), (total if rank == world - 1 else int(np.searchsorted(inst, ihi, "left")))
+    # shard by instance over the ranks (instance ids local to the rank's shard: every engine counts from 0)
+    from consensus_b200 import sharding
+    vlo, vhi, ilo, ihi, local_inst = sharding.shard_votes(inst, I, rank, world)
     sl = slice(vlo, vhi)
     F = {k: pin(rep4(tile[k])[sl]) for k in ("r", "s", "qx", "qy", "digest")}
-    cols = [pin(inst[sl] - np.uint32(ilo)), pin(sender[sl]), pin(signer[sl]), pin(dm[sl]), pin(self_id[ilo:ihi])]   # instance ids local to the rank's shard
+    cols = [pin(local_inst), pin(sender[sl]), pin(signer[sl]), pin(dm[sl]), pin(self_id[ilo:ihi])]
     nv, ni = vhi - vlo, ihi - ilo
     ok_h, cnt_h, rch_h = pin(np.zeros(nv, np.uint8)), pin(np.zeros(ni, np.uint32)), pin(np.zeros(ni, np.uint8))
     wi = (I // world + 1 + 31) // 32

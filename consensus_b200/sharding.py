@@ -23,6 +23,16 @@ def shard_instances(instance_ids: np.ndarray, n_instances: int, rank: int, world
     return (instance_ids >= lo) & (instance_ids < hi), lo, hi
 
 
+def shard_votes(instance_ids: np.ndarray, n_instances: int, rank: int, world: int):
+    """Vote range [vlo, vhi), instance range [ilo, ihi) and the SHARD-LOCAL instance ids of rank `rank` for a vote stream
+    grouped by non-decreasing instance id (the input contract of sbv_verify_quorum, whose instance ids count from 0 on
+    every engine).  The last rank also takes trailing votes whose instance id is out of range (padding)."""
+    ilo, ihi = shard_range(n_instances, rank, world)
+    vlo = int(np.searchsorted(instance_ids, ilo, "left"))
+    vhi = instance_ids.size if rank == world - 1 else int(np.searchsorted(instance_ids, ihi, "left"))
+    return vlo, vhi, ilo, ihi, (instance_ids[vlo:vhi] - np.uint32(ilo)).astype(np.uint32)
+
+
 def words_per_shard(n: int, world: int) -> int:
     return (((n + world - 1) // world) + 31) // 32
 

@@ -55,6 +55,11 @@ def _worker(rank, world, port, q):
         votes = list(zip(sender[sel].tolist(), signer[sel].tolist(), dm[sel].tolist(), sig_ok[sel].tolist()))
         want_r.append(int(ref.count_commit_votes(votes, self_id=0) >= q_ - 1))
     ok_quorum = reached.tolist() == want_r and bool(mask.sum() == (ihi - ilo) * (N - 1))
+    # the vote stream as sbv_verify_quorum takes it on a rank: shard-local instance ids, counts local to the shard
+    vlo, vhi, ilo2, ihi2, local_inst = sharding.shard_votes(inst, I, rank, world)
+    cnt2, _ = ref.count_commit_votes_batch(local_inst, sender[vlo:vhi], signer[vlo:vhi], dm[vlo:vhi], sig_ok[vlo:vhi], ihi2 - ilo2, q_ - 1,
+                                           np.zeros(ihi2 - ilo2, np.uint16))
+    ok_quorum = ok_quorum and (ilo2, ihi2) == (ilo, ihi) and cnt2.tolist() == counts_local.tolist() and vhi - vlo == int(mask.sum())
     if rank == 0:
         q.put((ok_verdicts, ok_quorum, int(want.sum())))
     dist.barrier()
