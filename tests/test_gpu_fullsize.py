@@ -124,6 +124,9 @@ def test_c4_quorum_stream_n16(eng):
     assert reached.tolist() == (want_cnt >= q - 1).astype(np.uint8).tolist()
     # at most f = 5 Byzantine votes per instance can never block a decision: Q-1 = 10 of 15 remain
     assert reached.all() and cnt.min() >= q - 1 and cnt.max() == votes_per
+    # one call: signatures verified and counted with the verdicts staying on the device (sbv_verify_quorum)
+    ok1, cnt1, reached1 = eng.verify_quorum(P256, r, s, qx, qy, dig, inst, sender, signer, digest_match, I, q - 1, self_id=np.zeros(I, np.uint16))
+    assert (ok1 == want_ok).all() and cnt1.tolist() == want_cnt.tolist() and reached1.tolist() == reached.tolist()
     # a stricter threshold separates the instances; thresholds are monotone
     _, reached13 = eng.quorum(inst, sender, signer, digest_match, got_ok, I, 13, self_id=np.zeros(I, np.uint16))
     assert reached13.tolist() == (want_cnt >= 13).astype(np.uint8).tolist()
