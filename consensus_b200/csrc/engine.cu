@@ -352,6 +352,7 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
     e->group_threshold = env_int("SBV_GROUP_THRESHOLD", 16);
     e->group_max_keys = env_int("SBV_GROUP_MAX_KEYS", 8192);
     e->group_min_batch = env_int("SBV_GROUP_MIN_BATCH", 0);
+    e->gsplit = env_int("SBV_GSPLIT", 1) != 0;
     {
         // per-engine hash seed: an adversary who picks the keys of a batch cannot aim at the probe sequence
         uint64_t t = (uint64_t)(uintptr_t)e;

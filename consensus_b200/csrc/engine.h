@@ -29,6 +29,7 @@ struct Dev {
         uint32_t *uw = nullptr;     // k_prep output: u1, u2 word-major [2N][cap]
         uint8_t *flags = nullptr;   // r, s range verdicts
         uint32_t *tscr = nullptr;   // k_verify_coz per-signature scratch: 12N words, word-major
+        uint32_t *gacc = nullptr;   // k_gpart -> k_verify_kt: u1*G of every item (Jacobian, 3N words, word-major)
         // key grouping
         uint32_t hsize = 0;
         uint32_t *htab = nullptr, *rep = nullptr, *keylist = nullptr, *klist = nullptr, *glist = nullptr;
@@ -42,7 +43,7 @@ struct Dev {
         bool used = false;
         bool open = false;  // taken by a launch whose second half has not been enqueued yet
         struct Caps {  // bytes allocated per buffer
-            size_t uw = 0, flags = 0, tscr = 0, htab = 0, rep = 0, keylist = 0, klist = 0, glist = 0, zeroed = 0, keyid = 0, item_kid = 0, bases = 0,
+            size_t uw = 0, flags = 0, tscr = 0, gacc = 0, htab = 0, rep = 0, keylist = 0, klist = 0, glist = 0, zeroed = 0, keyid = 0, item_kid = 0, bases = 0,
                    hs = 0, ztop = 0, pref = 0, ktab = 0, keyflags = 0;
         } caps;
     } ws[SBV_SCRATCH];
@@ -92,6 +93,7 @@ struct sbv_engine {
     int group_threshold = 16;      // a key gets a table when it occurs at least this often in a batch (SBV_GROUP_THRESHOLD; 0 = never)
     int group_max_keys = 8192;     // table slots per launch (SBV_GROUP_MAX_KEYS)
     int group_min_batch = 0;       // launches smaller than this skip the grouping (SBV_GROUP_MIN_BATCH)
+    bool gsplit = true;            // u1*G in its own kernel beside the table construction (SBV_GSPLIT=0: inside the fixed-base kernel)
     uint32_t hash_seed = 0x9e3779b9u;
     bool profiling = false;
     // NCCL (loaded lazily with dlopen so single-device, single-rank users never touch it)

@@ -38,6 +38,13 @@ cudaError_t op_group(uint32_t n, const uint8_t *qx, const uint8_t *qy, uint32_t 
 }
 
 template <class C>
+cudaError_t op_gpart(uint32_t n, const uint32_t *uw, const uint32_t *gtab, uint32_t *gacc, cudaStream_t st) {
+    constexpr int BLOCK = 64;
+    k_gpart<C, BLOCK, Cfg<C>::KT_MINB - 1><<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, st>>>(n, uw, reinterpret_cast<const uint4 *>(gtab), gacc);
+    return cudaGetLastError();
+}
+
+template <class C>
 cudaError_t op_coz(uint32_t n, const uint8_t *qx, const uint8_t *qy, const uint8_t *r, const uint32_t *uw, const uint8_t *flags,
                    const uint32_t *gtab, uint32_t *tscr, uint8_t *ok, const uint32_t *list, const uint32_t *count, cudaStream_t st) {
     constexpr int BLOCK = 64;
@@ -65,12 +72,12 @@ cudaError_t op_kt_build(const uint32_t *nkeys_ptr, uint32_t cap, const uint32_t 
 template <class C, int W>
 cudaError_t op_kt_verify(int reg, int warp, uint32_t n, const uint32_t *slot, const int32_t *kidmap, uint32_t n_slots,
                          const uint8_t *keyflags, const uint8_t *r, const uint32_t *uw, const uint8_t *flags, const uint32_t *gtab,
-                         const uint32_t *ktab, uint8_t *ok, const uint32_t *list, const uint32_t *count, cudaStream_t st) {
+                         const uint32_t *ktab, uint8_t *ok, const uint32_t *list, const uint32_t *count, const uint32_t *gacc, cudaStream_t st) {
     constexpr int BLOCK = 64, MINB = Cfg<C>::KT_MINB;
     static const int variant = getenv("SBV_KT_VARIANT") ? atoi(getenv("SBV_KT_VARIANT")) : Cfg<C>::KT_VARIANT;
     const uint4 *g4 = reinterpret_cast<const uint4 *>(gtab), *k4 = reinterpret_cast<const uint4 *>(ktab);
     const unsigned blocks = (n + BLOCK - 1) / BLOCK;
-#define SBV_KT_ARGS n, slot, kidmap, n_slots, keyflags, r, uw, flags, g4, k4, ok, list, count
+#define SBV_KT_ARGS n, slot, kidmap, n_slots, keyflags, r, uw, flags, g4, k4, ok, list, count, gacc
     if (warp) {
         k_verify_kt_warp<C, W><<<(unsigned)(((size_t)n * 32 + 127) / 128), 128, 0, st>>>(n, slot, kidmap, n_slots, keyflags, r, uw, flags, g4, k4, ok);
     } else if (reg) {

@@ -409,8 +409,32 @@ struct Inl : C {
 template <class C, bool INL> struct PickArith { using type = C; };
 template <class C> struct PickArith<C, true> { using type = Inl<C>; };
 
+// k_gpart — the u1*G half of a fixed-base verification on its own: needs only the scalars, so the grouped pipeline runs
+// it while the per-key tables are still being built; k_verify_kt<…, GSPLIT> then starts from the stored point.
+// gacc: [3N][n] words (X, Y, Z of item idx at column idx).
+template <class C, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_gpart(uint32_t n, const uint32_t *__restrict__ uw, const uint4 *__restrict__ gtab,
+                                                        uint32_t *__restrict__ gacc) {
+    constexpr int N = C::N;
+    const uint32_t idx = blockIdx.x * BLOCK + threadIdx.x;
+    if (idx >= n) return;
+    Jac<C> acc;
+    C::get_one(acc.X);
+    C::get_one(acc.Y);
+#pragma unroll
+    for (int i = 0; i < N; i++) acc.Z[i] = 0;
+    add_u1G<C>(acc, uw, n, idx, gtab);
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        gacc[(size_t)i * n + idx] = acc.X[i];
+        gacc[(size_t)(N + i) * n + idx] = acc.Y[i];
+        gacc[(size_t)(2 * N + i) * n + idx] = acc.Z[i];
+    }
+}
+
 // REG = true: registered keys (sbv_set_keys): the key of item i is kidmap[slot[i]].
 // REG = false: keys grouped on the fly: the key of item i is kidmap[i] (>= 0 for every listed item).
+// gacc != NULL: the u1*G half was computed by k_gpart; only the key's windows remain.
 // One loop over the NWIN windows of u2*Q and then the GWINS windows of u1*G: a single addition site, with the table
 // entry of the next window (a random 64-byte gather) in flight while the current one is added.
 template <class C, int W, int BLOCK, int MINB, bool REG, bool INL>
@@ -419,12 +443,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_verify_kt(uint32_t n, const uin
                                                             const uint8_t *__restrict__ r_be, const uint32_t *__restrict__ uw,
                                                             const uint8_t *__restrict__ flags, const uint4 *__restrict__ gtab,
                                                             const uint4 *__restrict__ ktab, uint8_t *__restrict__ ok_out,
-                                                            const uint32_t *__restrict__ list, const uint32_t *__restrict__ count) {
+                                                            const uint32_t *__restrict__ list, const uint32_t *__restrict__ count,
+                                                            const uint32_t *__restrict__ gacc) {
     using A = typename PickArith<C, INL>::type;  // arithmetic policy
     constexpr int N = C::N;
     constexpr int EU4 = 2 * N / 4;  // uint4 per table entry
     using KT = KeyTab<32 * N, W>;
-    constexpr int TOTAL = KT::NWIN + C::GWINS;
+    const int TOTAL = gacc ? KT::NWIN : KT::NWIN + C::GWINS;
     const uint32_t t = blockIdx.x * BLOCK + threadIdx.x;
     if (t >= (list ? __ldg(count) : n)) return;
     const uint32_t idx = list ? __ldg(list + t) : t;
@@ -442,10 +467,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_verify_kt(uint32_t n, const uin
     uint32_t one[N];
     C::get_one(one);
     Jac<A> acc;
-    mp_copy<N>(acc.X, one);
-    mp_copy<N>(acc.Y, one);
+    if (gacc) {
 #pragma unroll
-    for (int i = 0; i < N; i++) acc.Z[i] = 0;
+        for (int i = 0; i < N; i++) {
+            acc.X[i] = __ldg(gacc + (size_t)i * n + idx);
+            acc.Y[i] = __ldg(gacc + (size_t)(N + i) * n + idx);
+            acc.Z[i] = __ldg(gacc + (size_t)(2 * N + i) * n + idx);
+        }
+    } else {
+        mp_copy<N>(acc.X, one);
+        mp_copy<N>(acc.Y, one);
+#pragma unroll
+        for (int i = 0; i < N; i++) acc.Z[i] = 0;
+    }
     // window w < NWIN: signed digit of u2 into the key's table; w >= NWIN: comb digit of u1 into the table of G
     auto fetch = [&](int w, uint32_t (&x)[N], uint32_t (&y)[N], bool &neg, bool &skip) {
         if (w < KT::NWIN) {

@@ -19,7 +19,7 @@ struct KtOps {
     // fixed-base verification; reg: keys by slot (registered) or by item (grouped); warp: one signature per warp
     cudaError_t (*verify)(int reg, int warp, uint32_t n, const uint32_t *slot, const int32_t *kidmap, uint32_t n_slots,
                           const uint8_t *keyflags, const uint8_t *r, const uint32_t *uw, const uint8_t *flags, const uint32_t *gtab,
-                          const uint32_t *ktab, uint8_t *ok, const uint32_t *list, const uint32_t *count, cudaStream_t st);
+                          const uint32_t *ktab, uint8_t *ok, const uint32_t *list, const uint32_t *count, const uint32_t *gacc, cudaStream_t st);
 };
 
 struct CurveOps {
@@ -32,6 +32,8 @@ struct CurveOps {
     cudaError_t (*group)(uint32_t n, const uint8_t *qx, const uint8_t *qy, uint32_t seed, uint32_t hmask, uint32_t *htab, uint32_t *rep,
                          uint32_t *kcnt, uint32_t threshold, uint32_t max_keys, int32_t *keyid, uint32_t *keylist, int32_t *item_kid,
                          uint32_t *klist, uint32_t *glist, uint32_t *counters, cudaStream_t st);
+    // u1*G of every item into gacc[3N][n] (the half of the fixed-base verification that does not need the key tables)
+    cudaError_t (*gpart)(uint32_t n, const uint32_t *uw, const uint32_t *gtab, uint32_t *gacc, cudaStream_t st);
     cudaError_t (*coz)(uint32_t n, const uint8_t *qx, const uint8_t *qy, const uint8_t *r, const uint32_t *uw, const uint8_t *flags,
                        const uint32_t *gtab, uint32_t *tscr, uint8_t *ok, const uint32_t *list, const uint32_t *count, cudaStream_t st);
     const KtOps *kt5, *kt8;

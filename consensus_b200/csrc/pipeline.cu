@@ -49,6 +49,7 @@ int take_scratch(sbv_engine *e, Dev &d, const CurveOps &ops, const KtOps *kt, si
         {(void **)&w.uw, &c.uw, 2 * N * n * 4, 2 * N * ni * 4},
         {(void **)&w.flags, &c.flags, n, ni},
         {(void **)&w.tscr, &c.tscr, 12 * N * n * 4, 12 * N * ni * 4},
+        {(void **)&w.gacc, &c.gacc, g ? 3 * N * n * 4 : 0, 3 * N * ni * 4},
         {(void **)&w.htab, &c.htab, g ? (size_t)hsize * 4 : 0, (size_t)hs2 * 4},
         {(void **)&w.rep, &c.rep, g ? n * 4 : 0, ni * 4},
         {(void **)&w.klist, &c.klist, g ? n * 4 : 0, ni * 4},
@@ -101,7 +102,7 @@ cudaEvent_t *prof_take(sbv_engine *e, Dev &d) {
 
 void sbv_scratch_free(Dev &d) {
     for (auto &w : d.ws) {
-        void *ptrs[] = {w.uw, w.flags, w.tscr, w.htab, w.rep, w.keylist, w.klist, w.glist, w.zeroed, w.keyid, w.item_kid, w.bases, w.hs, w.ztop, w.pref, w.ktab, w.keyflags};
+        void *ptrs[] = {w.uw, w.flags, w.tscr, w.gacc, w.htab, w.rep, w.keylist, w.klist, w.glist, w.zeroed, w.keyid, w.item_kid, w.bases, w.hs, w.ztop, w.pref, w.ktab, w.keyflags};
         for (void *p : ptrs) if (p) cudaFree(p);
         cudaEvent_t evs[] = {w.done, w.ev_group, w.ev_prep, w.ev_tab, w.ev_gen};
         for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
@@ -186,9 +187,16 @@ int sbv_launch_verify_finish(sbv_engine *e, Dev &d, const VerifyLaunch &vl, cons
     CU(e, cudaStreamWaitEvent(w->s_gen, w->ev_prep, 0));
     CU(e, ops.coz(nn, vl.d_qx, vl.d_qy, d_r, w->uw, w->flags, gtab, w->tscr, d_ok, w->glist, counters + 2, w->s_gen));
     CU(e, cudaEventRecord(w->ev_gen, w->s_gen));
+    // the u1*G half needs no table: it runs while the tables are still being built
+    const uint32_t *gacc = nullptr;
+    if (e->gsplit) {
+        CU(e, ops.gpart(nn, w->uw, gtab, w->gacc, st));
+        gacc = w->gacc;
+        e->launches += 1;
+    }
     CU(e, cudaStreamWaitEvent(st, w->ev_tab, 0));
     if (ev) CU(e, cudaEventRecord(ev[2], st));
-    CU(e, kt->verify(0, 0, nn, nullptr, w->item_kid, 0, w->keyflags, d_r, w->uw, w->flags, gtab, w->ktab, d_ok, w->klist, counters + 1, st));
+    CU(e, kt->verify(0, 0, nn, nullptr, w->item_kid, 0, w->keyflags, d_r, w->uw, w->flags, gtab, w->ktab, d_ok, w->klist, counters + 1, gacc, st));
     if (ev) CU(e, cudaEventRecord(ev[3], st));
     CU(e, cudaStreamWaitEvent(st, w->ev_gen, 0));
     CU(e, cudaEventRecord(w->done, st));
@@ -286,7 +294,7 @@ int sbv_launch_keyed(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint3
     if (ev) { CU(e, cudaEventRecord(ev[1], st)); CU(e, cudaEventRecord(ev[2], st)); }
     const int warp = nn <= (uint32_t)e->keyed_warp_limit ? 1 : 0;  // small batch: one signature per warp (latency path)
     CU(e, kt->verify(1, warp, nn, d_slot, d.slot2local[curve], d.n_slots, d.keyflags[curve], d_r, w->uw, w->flags, d.gtab[curve], d.ktab[curve], d_ok,
-                     nullptr, nullptr, st));
+                     nullptr, nullptr, nullptr, st));
     if (ev) CU(e, cudaEventRecord(ev[3], st));
     CU(e, cudaEventRecord(w->done, st));
     e->launches += 2;

@@ -107,9 +107,12 @@ static void verify_grouped_t(uint32_t n, const uint8_t *r, const uint8_t *s, con
     run_grid((unsigned)((cap * KT::NWIN + 63) / 64), 64, [&] { k_kt_fill<C, W>(counters.data(), (uint32_t)cap, bases.data(), kflags.data(), hs.data(), ztop.data(), ktab.data()); });
     run_grid((unsigned)((cap + 63) / 64), 64, [&] { k_kt_inv<C, W>(counters.data(), (uint32_t)cap, kflags.data(), ztop.data(), pref.data()); });
     run_grid((unsigned)((cap * KT::NWIN + 63) / 64), 64, [&] { k_kt_final<C, W>(counters.data(), (uint32_t)cap, bases.data(), kflags.data(), hs.data(), ztop.data(), ktab.data()); });
+    const bool gsplit = (threshold & 1) == 0;  // exercise both forms: even thresholds take the split u1*G path
+    std::vector<uint32_t> gacc((size_t)3 * N * n);
+    if (gsplit) run_grid((n + 63) / 64, 64, [&] { k_gpart<C, 64, 1>(n, uw.data(), gtab, gacc.data()); });
     run_grid((n + 63) / 64, 64, [&] {
         k_verify_kt<C, W, 64, 1, false, false>(n, nullptr, item_kid.data(), 0, kflags.data(), r, uw.data(), flags.data(), gtab,
-                                        reinterpret_cast<const uint4 *>(ktab.data()), ok, klist.data(), counters.data() + 1);
+                                        reinterpret_cast<const uint4 *>(ktab.data()), ok, klist.data(), counters.data() + 1, gsplit ? gacc.data() : nullptr);
     });
     run_grid((n + 63) / 64, 64, [&] {
         k_verify_coz<C, 64, 1>(n, qx, qy, r, uw.data(), flags.data(), gtab, tscr.data(), ok, glist.data(), counters.data() + 2);
