@@ -6,7 +6,7 @@ work is fixed as N grows: weak scaling); with N > 1 every step ends with the all
 over NCCL, issued by the engine itself (sbv_gather_verdicts_device: k_pack_bits + ncclAllGather on the step's stream) —
 the only exchange the path has.  No PyTorch kernel runs inside a step.
 
-  value      device-timed, inputs already resident in HBM (16 rotating copies = 168 MB > L2), steps rotating over 3 streams
+  value      device-timed, inputs already resident in HBM (16 rotating copies = 168 MB > L2), steps rotating over 4 streams
   e2e        the same metric through the C ABI with pinned HOST buffers (sbv_verify_batch; sbv_verify_batch_ranked when
              N > 1, i.e. INCLUDING the gather): H2D of the 160 B/item batch and D2H of the verdicts inside the timed region
   roofline   dominant kernel (k_verify_kt: the fixed-base kernel the repeated keys of the batch take): achieved wide-MAC/s
@@ -39,7 +39,7 @@ MAC32_PER_VERIFY = 272_256       # SURVEY.md §8d canonical count (P-256)
 MAC32_PER_VERIFY_P384 = 902_880
 BYTES_PER_VERIFY = 161           # 160 B in + 1 B out
 N_COPIES = 16                    # rotating input copies: 16 x 10.5 MB > 126 MB L2
-N_LANES = 3
+N_LANES = 4
 METRIC = "ECDSA-P256 verifies/sec at batch=64K"
 WORKLOAD = "C2: ECDSA-P256 batch verify, 65,536 synthetic sigs per GPU, 1,024 keys, 1/16 corrupted"
 
@@ -208,7 +208,7 @@ def main():
     d_ok = torch.zeros(BATCH, dtype=torch.uint8, device=dev)
     words = BATCH // 32
     stream = torch.cuda.current_stream().cuda_stream
-    # Consecutive steps are independent batches, so they are enqueued round-robin on three streams: the latency-bound
+    # Consecutive steps are independent batches, so they are enqueued round-robin on four streams: the latency-bound
     # heads of step i+1 (key grouping, table construction, scalar preparation) overlap the verify kernel of step i.
     # Every step still does all of its work; the timed region is bracketed by events on the main stream that wait for all.
     lanes = [torch.cuda.Stream(device=dev) for _ in range(N_LANES)]
