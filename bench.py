@@ -401,7 +401,7 @@ def main():
     mac_rate = BATCH * MAC32_PER_VERIFY / (k_ms * 1e-3)
     roofline = {
         "bound": "int32-mad (IMAD.WIDE issue rate; neither hbm nor tensor binds this path)",
-        "kernel": "k_verify_kt<P256,5> (fixed-base kernel of the key-grouped pipeline)", "achieved": mac_rate / 1e12, "peak": mad_peak / 1e12,
+        "kernel": "k_gpart + k_verify_kt<P256,5> (the two halves of the fixed-base verification of the key-grouped pipeline: u1*G, then the key's windows)", "achieved": mac_rate / 1e12, "peak": mad_peak / 1e12,
         "unit": "TMAC32/s", "frac": mac_rate / mad_peak if mad_peak else None, "peak_source": "sbv_probe_mad_rate, same run",
         "kernel_ms": k_ms, "prep_and_grouping_ms": prep_ms / max(pairs, 1), "step_latency_ms": step_latency_ms,
         "frac_whole_step_isolated": BATCH * MAC32_PER_VERIFY / (step_latency_ms * 1e-3) / mad_peak if mad_peak else None,

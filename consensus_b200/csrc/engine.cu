@@ -628,7 +628,7 @@ int sbv_profile_enable(sbv_engine *e, int on) {
 }
 
 // Sums the recorded intervals (all devices), then resets: prep_ms = start .. end of k_prep (includes the key grouping),
-// verify_ms = the dominant verify kernel alone (k_verify_kt when keys were grouped, k_verify_coz otherwise).
+// verify_ms = the verification kernels alone (k_gpart + k_verify_kt when keys were grouped, k_verify_coz otherwise).
 // The caller must have synchronised the streams it used.
 int sbv_profile_read(sbv_engine *e, double *prep_ms, double *verify_ms, uint64_t *n_launches) {
     if (!e) return SBV_ERR_ARG;
@@ -637,12 +637,13 @@ int sbv_profile_read(sbv_engine *e, double *prep_ms, double *verify_ms, uint64_t
     uint64_t cnt = 0;
     for (Dev &d : e->devs) {
         CU(e, cudaSetDevice(d.ordinal));
-        for (size_t i = 0; i + 3 < d.prof_used && i + 3 < d.prof_events.size(); i += 4) {
-            float a = 0, b = 0;
+        for (size_t i = 0; i + 4 < d.prof_used && i + 4 < d.prof_events.size(); i += 5) {
+            float a = 0, b = 0, g = 0;
             CU(e, cudaEventSynchronize(d.prof_events[i + 3]));
             CU(e, cudaEventElapsedTime(&a, d.prof_events[i], d.prof_events[i + 1]));
             CU(e, cudaEventElapsedTime(&b, d.prof_events[i + 2], d.prof_events[i + 3]));
-            p += a; v += b; cnt++;
+            CU(e, cudaEventElapsedTime(&g, d.prof_events[i + 1], d.prof_events[i + 4]));  // k_gpart (0 without the split)
+            p += a; v += b + g; cnt++;
         }
         d.prof_used = 0;
     }

@@ -87,14 +87,14 @@ int take_scratch(sbv_engine *e, Dev &d, const CurveOps &ops, const KtOps *kt, si
 
 cudaEvent_t *prof_take(sbv_engine *e, Dev &d) {
     if (!e->profiling) return nullptr;
-    if (d.prof_used + 4 > d.prof_events.size()) {
+    if (d.prof_used + 5 > d.prof_events.size()) {
         size_t old = d.prof_events.size();
         d.prof_events.resize(old + 128);
         for (size_t i = old; i < d.prof_events.size(); i++)
             if (cudaEventCreate(&d.prof_events[i]) != cudaSuccess) { d.prof_events.resize(i); return nullptr; }
     }
     cudaEvent_t *ev = &d.prof_events[d.prof_used];
-    d.prof_used += 4;
+    d.prof_used += 5;  // start, after prep, before / after the fixed-base (or generic) kernel, after k_gpart
     return ev;
 }
 
@@ -173,7 +173,7 @@ int sbv_launch_verify_finish(sbv_engine *e, Dev &d, const VerifyLaunch &vl, cons
     const uint32_t *gtab = d.gtab[vl.curve];
     CU(e, ops.prep(nn, d_r, d_s, d_dig, dlen, w->uw, w->flags, st));
     if (!vl.grouping) {
-        if (ev) { CU(e, cudaEventRecord(ev[1], st)); CU(e, cudaEventRecord(ev[2], st)); }
+        if (ev) { CU(e, cudaEventRecord(ev[1], st)); CU(e, cudaEventRecord(ev[4], st)); CU(e, cudaEventRecord(ev[2], st)); }
         CU(e, ops.coz(nn, vl.d_qx, vl.d_qy, d_r, w->uw, w->flags, gtab, w->tscr, d_ok, nullptr, nullptr, st));
         if (ev) CU(e, cudaEventRecord(ev[3], st));
         CU(e, cudaEventRecord(w->done, st));
@@ -194,6 +194,7 @@ int sbv_launch_verify_finish(sbv_engine *e, Dev &d, const VerifyLaunch &vl, cons
         gacc = w->gacc;
         e->launches += 1;
     }
+    if (ev) CU(e, cudaEventRecord(ev[4], st));  // == ev[1] without the split
     CU(e, cudaStreamWaitEvent(st, w->ev_tab, 0));
     if (ev) CU(e, cudaEventRecord(ev[2], st));
     CU(e, kt->verify(0, 0, nn, nullptr, w->item_kid, 0, w->keyflags, d_r, w->uw, w->flags, gtab, w->ktab, d_ok, w->klist, counters + 1, gacc, st));
@@ -291,7 +292,7 @@ int sbv_launch_keyed(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint3
     cudaEvent_t *ev = prof_take(e, d);
     if (ev) CU(e, cudaEventRecord(ev[0], st));
     CU(e, ops.prep(nn, d_r, d_s, d_dig, dlen, w->uw, w->flags, st));
-    if (ev) { CU(e, cudaEventRecord(ev[1], st)); CU(e, cudaEventRecord(ev[2], st)); }
+    if (ev) { CU(e, cudaEventRecord(ev[1], st)); CU(e, cudaEventRecord(ev[4], st)); CU(e, cudaEventRecord(ev[2], st)); }
     const int warp = nn <= (uint32_t)e->keyed_warp_limit ? 1 : 0;  // small batch: one signature per warp (latency path)
     CU(e, kt->verify(1, warp, nn, d_slot, d.slot2local[curve], d.n_slots, d.keyflags[curve], d_r, w->uw, w->flags, d.gtab[curve], d.ktab[curve], d_ok,
                      nullptr, nullptr, nullptr, st));

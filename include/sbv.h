@@ -185,7 +185,8 @@ void sbv_host_free(void *p);
 uint64_t sbv_kernel_launches(const sbv_engine *e);
 /* Optional CUDA-event timing inside every verify launch (off by default).  sbv_profile_read sums, over all
  * devices, prep_ms = launch start .. end of the scalar preparation (includes the key grouping) and verify_ms = the
- * dominant verify kernel alone (the fixed-base kernel when keys were grouped, the generic one otherwise), and
+ * verification kernels alone (the two halves of the fixed-base verification when keys were grouped, the generic kernel
+ * otherwise), and
  * resets; the caller synchronises the streams it used first. */
 int sbv_profile_enable(sbv_engine *e, int on);
 int sbv_profile_read(sbv_engine *e, double *prep_ms, double *verify_ms, uint64_t *n_launch_pairs);
