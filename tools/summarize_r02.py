@@ -29,21 +29,21 @@ if os.path.exists(p):
         agg.setdefault(name, []).append(float(r[vi].replace(",", "")))
     step = {k: v for k, v in agg.items() if k.startswith("k_") and "gtable" not in k and "mad_probe" not in k}
     tot = sum(sum(v) / len(v) for v in step.values())
-    lines = [f"# ncu launch list ({tag}): ncu --metrics gpu__time_duration.sum --clock-control none -c 150  python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras",
+    lines = [f"# ncu launch list ({tag}): ncu --metrics gpu__time_duration.sum --clock-control none -c 170  python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras",
              "# per-launch times are cold-cache and serialised: compare SHARES of a step (one launch of each kernel), not absolutes", "",
              f"{'kernel':44s} {'launches':>8s} {'avg_us':>10s} {'share_of_step':>14s}"]
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1]) / len(kv[1])):
         share = f"{sum(v)/len(v)/tot:13.1%}" if k in step else "   (not in step)"
         lines.append(f"{k[:44]:44s} {len(v):8d} {sum(v)/len(v)/1e3:10.1f} {share}")
-    lines += ["", "# critical path of an ISOLATED step: grouping -> bases -> fill -> inv -> final -> k_verify_kt (k_prep and k_verify_coz run beside it);",
+    lines += ["", "# critical path of an ISOLATED step: grouping -> bases -> fill -> inv -> final -> k_verify_kt (k_prep, k_gpart and k_verify_coz run beside the table kernels);",
               "# pipelined steps overlap the latency-bound table kernels of step i+1 with the k_verify_kt of step i"]
     open(os.path.join(out, f"{tag}_launches.txt"), "w").write("\n".join(lines) + "\n")
 
-# ---- ncu --set full of the dominant kernel ----
+# ---- ncu --set full of the verification kernels (k_gpart + k_verify_kt) ----
 rep = os.path.join(go, f"{visit}_prof_kt.ncu-rep")
 if os.path.exists(rep):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rr = list(csv.reader(raw.splitlines())); h, u, v = rr[0], rr[1], rr[2]
+    rr = list(csv.reader(raw.splitlines())); h, u = rr[0], rr[1]
     want = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor",
             "launch__occupancy_limit", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "smsp__issue_active.avg.per_cycle_active",
             "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
@@ -51,16 +51,25 @@ if os.path.exists(rep):
             "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
             "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "smsp__average_warps_issue_stalled", "sm__cycles_elapsed.avg", "sass__inst_executed_local"]
-    sel = [f"# ncu --set full --clock-control none --import-source on -k regex:k_verify_kt -s 4 -c 1 ({tag}); kernel: {v[h.index('Kernel Name')][:60]}", ""]
-    vals = {}
-    for a, b, c in zip(h, u, v):
-        if any(w in a for w in want) and ".max" not in a and ".min" not in a and "pcsamp" not in a and "per_second" not in a and "Triage" not in a:
-            sel.append(f"{a:92s} {c:>18s} {b}")
-            vals[a] = (c, b)
-    open(os.path.join(out, f"{tag}_k_verify_kt_ncu.txt"), "w").write("\n".join(sel) + "\n")
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tr = sum(float(vals[k][0]) * scale[vals[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    json.dump({"dram_bytes_per_launch": tr, "kernel": "k_verify_kt<P256,5>", "source": f"profiles/{tag}_k_verify_kt_ncu.txt (ncu --set full, one launch of the 65,536-signature batch)"},
+    sel = [f"# ncu --set full --clock-control none --import-source on -k 'regex:k_verify_kt|k_gpart' -s 8 -c 2 ({tag}): the two halves of the fixed-base",
+           "# verification of one 65,536-signature step (python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras)", ""]
+    tr, names = 0.0, []
+    for v in rr[2:]:
+        if len(v) != len(h):
+            continue
+        kn = v[h.index("Kernel Name")]
+        names.append(kn.split("(")[0])
+        sel += [f"## {kn[:100]}", ""]
+        vals = {}
+        for a, b, c in zip(h, u, v):
+            if any(w in a for w in want) and ".max" not in a and ".min" not in a and "pcsamp" not in a and "per_second" not in a and "Triage" not in a:
+                sel.append(f"{a:92s} {c:>18s} {b}")
+                vals[a] = (c, b)
+        sel.append("")
+        tr += sum(float(vals[k][0]) * scale[vals[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum") if k in vals)
+    open(os.path.join(out, f"{tag}_k_verify_kt_ncu.txt"), "w").write("\n".join(sel) + "\n")
+    json.dump({"dram_bytes_per_launch": tr, "kernels": names, "source": f"profiles/{tag}_k_verify_kt_ncu.txt (ncu --set full, k_gpart + k_verify_kt of one 65,536-signature step)"},
               open(os.path.join(out, f"{tag}_traffic.json"), "w"))
 
 # ---- SASS opcode histograms (from the in-tree build: nothing GPU-side) ----
