@@ -208,7 +208,13 @@ static __device__ __noinline__ Fe12 p384_nmul_call(Fe12 a, Fe12 b);
 struct P384 {
     static constexpr int N = 12;
     static constexpr int BYTES = 48;
-    static constexpr int GW = 8;               // 48 windows x 256 entries (a 16-bit comb would be 151 MB)
+#ifndef SBV_P384_GW
+#define SBV_P384_GW 16
+#endif
+    // fixed-base comb of G: 24 windows x 65,536 entries = 151 MB in HBM (not L2-resident like P-256's 64 MB, but the
+    // gather of the next entry is in flight during the current addition and a P-384 addition takes microseconds);
+    // 24 additions per verify instead of the 48 of an 8-bit comb.  The CPU simulation of tests/ builds an 8-bit one.
+    static constexpr int GW = SBV_P384_GW;
     static constexpr int GWINS = 384 / GW;
 
     SBV_DEV static void get_p(uint32_t (&r)[12]) { const uint32_t c[12] = SBV_P384_P; mp_copy<12>(r, c); }

@@ -1,7 +1,7 @@
 // kernels.cuh — sm_100a kernels of the sbv hot path (ECDSA verify over NIST prime curves).
 //
 //   k_gtable_init        one-time: affine fixed-base comb table  T[i][b] = b * 2^(GW*i) * G  (Montgomery form;
-//                        GW = 16 for P-256: 64 MiB, L2-resident; GW = 8 for P-384)
+//                        GW = 16 for both curves: 64 MiB for P-256, L2-resident; 151 MB for P-384, in HBM)
 //   k_prep               per batch: range checks, batched inversion of s mod n (Montgomery's trick over S items
 //                        per thread, one binary-extended-GCD inversion per thread), u1 = e/s, u2 = r/s written
 //                        word-major ([2N][n] words) so that every consumer reads them coalesced and cuts its own
