@@ -193,7 +193,7 @@ def main():
     eng = sbv.Engine(devices=[local_rank])
     # one-process-per-GPU: the engines form their own NCCL communicators (one channel per concurrent stream / caller);
     # torch.distributed only carries the 128-byte ids and the final max-over-ranks
-    n_channels = N_LANES + 4
+    n_channels = N_LANES + int(os.environ.get("SBV_BENCH_E2E_THREADS", "4"))
     if world > 1:
         for ch in range(n_channels):
             uid = torch.zeros(128, dtype=torch.uint8, device=dev)
@@ -308,7 +308,7 @@ def main():
     # Host threads each keep one synchronous call in flight (the reference calls its Verifier from concurrent goroutines,
     # view.go:537-541 / consensus.go:302-306); every call does H2D of its 160 B/item batch, the whole pipeline and the
     # D2H of its verdicts — and, with N > 1, the NCCL all-gather of the packed verdicts plus the D2H of the gathered mask.
-    E2E_THREADS = 4
+    E2E_THREADS = int(os.environ.get("SBV_BENCH_E2E_THREADS", "4"))
     ptr = {k: host[k].data_ptr() for k in fields}
     host_oks = [torch.zeros(BATCH, dtype=torch.uint8).pin_memory() for _ in range(E2E_THREADS)]
     host_masks = [torch.zeros(world * words, dtype=torch.int32).pin_memory() for _ in range(E2E_THREADS)]
@@ -483,7 +483,7 @@ def run_extras(eng, sbv, oracle, np, torch, dev, rank, world, local_rank, mad_pe
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
 
     def best_of(fn, reps=3):
-        for _ in range(6):      # one warm-up call per scratch set of the engine (each grows its buffers on first use)
+        for _ in range(8):      # one warm-up call per scratch set of the engine (each grows its buffers on first use)
             fn()
         best = 1e30
         for _ in range(reps):

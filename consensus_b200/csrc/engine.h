@@ -14,8 +14,8 @@
 #include "../../include/sbv.h"
 #include "ops.h"
 
-constexpr int SBV_LANES = 4;    // concurrent host-buffer calls per engine
-constexpr int SBV_SCRATCH = 6;  // scratch sets per device (> SBV_LANES + 1: a launch may be held open per lane)
+constexpr int SBV_LANES = 6;    // concurrent host-buffer calls per engine
+constexpr int SBV_SCRATCH = 8;  // scratch sets per device (> SBV_LANES + 1: a launch may be held open per lane)
 
 struct Dev {
     int ordinal = 0;

@@ -60,9 +60,10 @@ cudaError_t op_kt_build(const uint32_t *nkeys_ptr, uint32_t cap, const uint32_t 
     using KT = KeyTab<32 * C::N, W>;
     const unsigned kb = (cap + 63) / 64;
     const unsigned wb = (unsigned)(((size_t)cap * KT::NWIN + 63) / 64);
-    static const bool bases_call = getenv("SBV_KT_BASES_CALL") != nullptr;  // A/B: out-of-line multiplications in the doubling chain
-    if (bases_call) k_kt_bases<C, W, false><<<kb, 64, 0, st>>>(nkeys_ptr, cap, keylist, qx, qy, bases, keyflags);
-    else k_kt_bases<C, W, true><<<kb, 64, 0, st>>>(nkeys_ptr, cap, keylist, qx, qy, bases, keyflags);
+    static const int bases_variant = getenv("SBV_KT_BASES") ? atoi(getenv("SBV_KT_BASES")) : 1;  // A/B: 1 = one thread per key (inlined), 2 = (out of line)
+    if (bases_variant == 2) k_kt_bases<C, W, false><<<kb, 64, 0, st>>>(nkeys_ptr, cap, keylist, qx, qy, bases, keyflags);
+    else if (bases_variant == 1) k_kt_bases<C, W, true><<<kb, 64, 0, st>>>(nkeys_ptr, cap, keylist, qx, qy, bases, keyflags);
+    else k_kt_bases4<C, W><<<(unsigned)(((size_t)cap * 4 + 127) / 128), 128, 0, st>>>(nkeys_ptr, cap, keylist, qx, qy, bases, keyflags);
     k_kt_fill<C, W><<<wb, 64, 0, st>>>(nkeys_ptr, cap, bases, keyflags, hs, ztop, ktab);
     k_kt_inv<C, W><<<kb, 64, 0, st>>>(nkeys_ptr, cap, keyflags, ztop, pref);
     k_kt_final<C, W><<<wb, 64, 0, st>>>(nkeys_ptr, cap, bases, keyflags, hs, ztop, ktab);

@@ -9,7 +9,8 @@
 //                 full-key compare on collision): rep[i] = first item with the same key; warp-aggregated count
 //   k_kg_assign   representatives whose key occurs >= T times (and while table slots last) get a dense key id
 //   k_kg_route    items are appended to the fixed-base list (their key has a table) or to the generic list
-//   k_kt_bases    one thread per key: validate the key, B_w = 2^(W*w) * Q for all windows (a chain of doublings)
+//   k_kt_bases4   four lanes per key: validate the key, B_w = 2^(W*w) * Q for all windows — a chain of doublings whose
+//                 independent multiplications run on different lanes (k_kt_bases: the one-thread-per-key form)
 //   k_kt_fill     one thread per (key, window): e*B_w for e = 1..2^(W-1) with co-Z additions (5M+2S each — the
 //                 chain of Z ratios that comes with them is exactly what the inversion needs)
 //   k_kt_inv      one thread per key: ONE field inversion for all windows of the key (Montgomery's trick across
@@ -159,6 +160,86 @@ __global__ void __launch_bounds__(64) k_kt_bases(const uint32_t *__restrict__ nk
         uint32_t *o = bases + (size_t)win * 3 * N * cap + k;
 #pragma unroll
         for (int i = 0; i < N; i++) { o[(size_t)i * cap] = B.X[i]; o[(size_t)(N + i) * cap] = B.Y[i]; o[(size_t)(2 * N + i) * cap] = B.Z[i]; }
+    }
+}
+
+// k_kt_bases4 — the same chain with FOUR LANES PER KEY (three of them working): the eight multiplications of a doubling
+// form four dependent levels, and the independent ones of a level run on different lanes:
+//   level 1   lane 0: delta = Z*Z          lane 1: bb = (2Y)*(2Y)        lane 2: Z3 = (2Y)*Z
+//   level 2   lane 0: (X-delta)*(X+delta)  lane 1: beta4 = X*bb          lane 2: bb*bb
+//   level 3   lane 0: alpha*alpha          (alpha = 3*(X-delta)(X+delta))
+//   level 4   lane 0: alpha*(beta4 - X3)
+// with six 8-word quad broadcasts per doubling (bb, beta4, 8Y^4, and the new X, Y, Z).  The kernel is one dependent
+// chain on an otherwise idle sub-partition, so halving the number of dependent multiplications halves its duration.
+template <class C, int W>
+__global__ void __launch_bounds__(128) k_kt_bases4(const uint32_t *__restrict__ nkeys_ptr, uint32_t cap, const uint32_t *__restrict__ keylist,
+                                                   const uint8_t *__restrict__ qx_be, const uint8_t *__restrict__ qy_be,
+                                                   uint32_t *__restrict__ bases, uint8_t *__restrict__ keyflags) {
+    constexpr int N = C::N;
+    using KT = KeyTab<32 * N, W>;
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t k = gt >> 2, role = gt & 3;
+    uint32_t nkeys = __ldg(nkeys_ptr);
+    if (nkeys > cap) nkeys = cap;
+    if (k >= nkeys) return;  // a quad leaves together
+    const unsigned qbase = (threadIdx.x & 31) & ~3u, qmask = 0xFu << qbase;
+    const uint32_t item = keylist ? keylist[k] : k;
+    uint32_t X[N], Y[N], Z[N];
+    const bool good = load_key<C>(X, Y, qx_be, qy_be, item);  // the four lanes agree
+    if (role == 0) keyflags[k] = good ? 1 : 0;
+    if (!good) return;
+    C::get_one(Z);
+    auto bcast = [&](uint32_t (&v)[N], unsigned src) {
+#pragma unroll
+        for (int i = 0; i < N; i++) v[i] = __shfl_sync(qmask, v[i], qbase + src);
+    };
+#pragma unroll 1
+    for (int win = 0; win < KT::NWIN; win++) {
+        if (win) {
+#pragma unroll 1
+            for (int d = 0; d < W; d++) {
+                uint32_t s[N], a[N], b[N], r1[N], r2[N], r3[N], r4[N], t1[N], t2[N];
+                C::fadd(s, Y, Y);
+                // level 1: delta | bb | Z3 | (delta)
+                mp_select<N>(a, role == 1 || role == 2, s, Z);
+                mp_select<N>(b, role == 1, s, Z);
+                C::fmul(r1, a, b);
+                uint32_t bb[N];
+                mp_copy<N>(bb, r1);
+                bcast(bb, 1);
+                // level 2: (X-delta)(X+delta) | X*bb | bb*bb
+                C::fsub(t1, X, r1);
+                C::fadd(t2, X, r1);
+                mp_select<N>(a, role == 0, t1, X);
+                mp_select<N>(a, role == 2, bb, a);
+                mp_select<N>(b, role == 0, t2, bb);
+                C::fmul(r2, a, b);
+                // level 3 (lane 0): alpha = 3*r2, alpha^2 ; lane 2: 8Y^4 = r2 / 2 ; lane 1 holds beta4 = r2
+                uint32_t alpha[N], half[N], beta4[N];
+                C::fadd(t1, r2, r2);
+                C::fadd(alpha, t1, r2);
+                C::fhalf(half, r2);
+                C::fmul(r3, alpha, alpha);
+                mp_copy<N>(beta4, r2);
+                bcast(beta4, 1);
+                bcast(half, 2);
+                // level 4 (lane 0): X3 = alpha^2 - 2*beta4 ; Y3 = alpha*(beta4 - X3) - 8Y^4
+                uint32_t x3[N], y3[N];
+                C::fadd(t1, beta4, beta4);
+                C::fsub(x3, r3, t1);
+                C::fsub(t2, beta4, x3);
+                C::fmul(r4, alpha, t2);
+                C::fsub(y3, r4, half);
+                mp_copy<N>(X, x3); bcast(X, 0);
+                mp_copy<N>(Y, y3); bcast(Y, 0);
+                mp_copy<N>(Z, r1); bcast(Z, 2);
+            }
+        }
+        if (role == 0) {
+            uint32_t *o = bases + (size_t)win * 3 * N * cap + k;
+#pragma unroll
+            for (int i = 0; i < N; i++) { o[(size_t)i * cap] = X[i]; o[(size_t)(N + i) * cap] = Y[i]; o[(size_t)(2 * N + i) * cap] = Z[i]; }
+        }
     }
 }
 
