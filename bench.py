@@ -184,16 +184,17 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # the only collectives of this path are KiB-sized bitmask gathers: one NCCL channel (one CTA) is plenty, and a
-        # one-CTA kernel is scheduled at once even while verify kernels fill the SMs (an operator's own setting wins)
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
         dist.init_process_group("nccl", device_id=dev)
 
     b = make_workload(rank)
     eng = sbv.Engine(devices=[local_rank])
     # one-process-per-GPU: the engines form their own NCCL communicators (one channel per concurrent stream / caller);
     # torch.distributed only carries the 128-byte ids and the final max-over-ranks
-    n_channels = N_LANES + int(os.environ.get("SBV_BENCH_E2E_THREADS", "4"))
+    # caller threads of the e2e leg: four keep one GPU busy; on the 8-GPU box three measured better than four
+    # (profiles/r02_scaling.txt: the ranks' synchronous calls meet in a gather every call, and more callers per rank made
+    # the slowest rank slower), so N = 8 runs with three
+    e2e_threads = int(os.environ.get("SBV_BENCH_E2E_THREADS", "4" if world <= 4 else "3"))
+    n_channels = N_LANES + e2e_threads
     if world > 1:
         for ch in range(n_channels):
             uid = torch.zeros(128, dtype=torch.uint8, device=dev)
@@ -308,7 +309,7 @@ def main():
     # Host threads each keep one synchronous call in flight (the reference calls its Verifier from concurrent goroutines,
     # view.go:537-541 / consensus.go:302-306); every call does H2D of its 160 B/item batch, the whole pipeline and the
     # D2H of its verdicts — and, with N > 1, the NCCL all-gather of the packed verdicts plus the D2H of the gathered mask.
-    E2E_THREADS = int(os.environ.get("SBV_BENCH_E2E_THREADS", "4"))
+    E2E_THREADS = e2e_threads
     ptr = {k: host[k].data_ptr() for k in fields}
     host_oks = [torch.zeros(BATCH, dtype=torch.uint8).pin_memory() for _ in range(E2E_THREADS)]
     host_masks = [torch.zeros(world * words, dtype=torch.int32).pin_memory() for _ in range(E2E_THREADS)]

@@ -209,7 +209,7 @@ struct P384 {
     static constexpr int N = 12;
     static constexpr int BYTES = 48;
 #ifndef SBV_P384_GW
-#define SBV_P384_GW 8
+#define SBV_P384_GW 16
 #endif
     // fixed-base comb of G: 24 windows x 65,536 entries = 151 MB in HBM (not L2-resident like P-256's 64 MB, but the
     // gather of the next entry is in flight during the current addition and a P-384 addition takes microseconds);

@@ -500,10 +500,6 @@ int sbv_comm_init_rank(sbv_engine *e, const uint8_t *id128, int nranks, int rank
     if (!e || !id128 || nranks < 1 || rank < 0 || rank >= nranks || e->devs.size() != 1)
         return fail(e, SBV_ERR_ARG, "sbv_comm_init_rank: bad argument (needs a single-device engine)");
     if (!e->rank_comms.empty() && (e->nranks != nranks || e->rank != rank)) return fail(e, SBV_ERR_ARG, "sbv_comm_init_rank: rank / nranks changed");
-    // The collectives of this path move a few KiB: one channel (one CTA) per communicator is plenty, and a one-CTA
-    // kernel finds a free SM slot at once even while the verify kernels of the other lanes fill the machine.
-    // Only a default: an operator's own setting wins.
-    setenv("NCCL_MAX_NCHANNELS", "1", 0);
     if (int rc = nccl_load(e)) return rc;
     Dev &d = e->devs[0];
     CU(e, cudaSetDevice(d.ordinal));

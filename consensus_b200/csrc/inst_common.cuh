@@ -60,7 +60,7 @@ cudaError_t op_kt_build(const uint32_t *nkeys_ptr, uint32_t cap, const uint32_t 
     using KT = KeyTab<32 * C::N, W>;
     const unsigned kb = (cap + 63) / 64;
     const unsigned wb = (unsigned)(((size_t)cap * KT::NWIN + 63) / 64);
-    static const int bases_variant = getenv("SBV_KT_BASES") ? atoi(getenv("SBV_KT_BASES")) : 1;  // A/B: 1 = one thread per key (inlined), 2 = (out of line)
+    static const int bases_variant = getenv("SBV_KT_BASES") ? atoi(getenv("SBV_KT_BASES")) : 0;  // A/B: 1 = one thread per key (inlined), 2 = (out of line)
     if (bases_variant == 2) k_kt_bases<C, W, false><<<kb, 64, 0, st>>>(nkeys_ptr, cap, keylist, qx, qy, bases, keyflags);
     else if (bases_variant == 1) k_kt_bases<C, W, true><<<kb, 64, 0, st>>>(nkeys_ptr, cap, keylist, qx, qy, bases, keyflags);
     else k_kt_bases4<C, W><<<(unsigned)(((size_t)cap * 4 + 127) / 128), 128, 0, st>>>(nkeys_ptr, cap, keylist, qx, qy, bases, keyflags);

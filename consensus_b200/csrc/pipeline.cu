@@ -68,14 +68,30 @@ int take_scratch(sbv_engine *e, Dev &d, const CurveOps &ops, const KtOps *kt, si
     bool grows = false;
     for (const Need &nd : needs) grows = grows || nd.need > *nd.cap;
     if (grows) {
-        if (w.used) CU(e, cudaEventSynchronize(w.done));  // nothing may still be using the buffers we are about to free
-        for (const Need &nd : needs) {
-            if (nd.need <= *nd.cap) continue;
-            if (*nd.p) cudaFree(*nd.p);
-            *nd.p = nullptr;
-            *nd.cap = 0;
-            CU(e, cudaMalloc(nd.p, nd.alloc));
-            *nd.cap = nd.alloc;
+        // Grow EVERY scratch set of the device now, not just this one: otherwise the first launch on each of the other sets
+        // would stop to allocate in the middle of a steady stream of launches (cudaMalloc of hundreds of MB synchronises).
+        for (int j = 0; j < SBV_SCRATCH; j++) {
+            Dev::Scratch &x = d.ws[j];
+            if (x.open && &x != &w) continue;  // held by a launch between its halves: it grows when it is next taken
+            if (x.used && x.done) CU(e, cudaEventSynchronize(x.done));  // nothing may still be using the buffers we are about to free
+            Dev::Scratch::Caps &cx = x.caps;
+            struct Slot { void **p; size_t *cap; };
+            const Slot slots[] = {
+                {(void **)&x.uw, &cx.uw}, {(void **)&x.flags, &cx.flags}, {(void **)&x.tscr, &cx.tscr}, {(void **)&x.gacc, &cx.gacc},
+                {(void **)&x.htab, &cx.htab}, {(void **)&x.rep, &cx.rep}, {(void **)&x.klist, &cx.klist}, {(void **)&x.glist, &cx.glist},
+                {(void **)&x.zeroed, &cx.zeroed}, {(void **)&x.keyid, &cx.keyid}, {(void **)&x.item_kid, &cx.item_kid}, {(void **)&x.keylist, &cx.keylist},
+                {(void **)&x.keyflags, &cx.keyflags}, {(void **)&x.bases, &cx.bases}, {(void **)&x.hs, &cx.hs}, {(void **)&x.ztop, &cx.ztop},
+                {(void **)&x.pref, &cx.pref}, {(void **)&x.ktab, &cx.ktab},
+            };
+            static_assert(sizeof(slots) / sizeof(slots[0]) == sizeof(needs) / sizeof(needs[0]), "one slot per buffer");
+            for (size_t q = 0; q < sizeof(slots) / sizeof(slots[0]); q++) {
+                if (needs[q].need <= *slots[q].cap) continue;
+                if (*slots[q].p) cudaFree(*slots[q].p);
+                *slots[q].p = nullptr;
+                *slots[q].cap = 0;
+                CU(e, cudaMalloc(slots[q].p, needs[q].alloc));
+                *slots[q].cap = needs[q].alloc;
+            }
         }
     }
     w.hsize = hsize;
