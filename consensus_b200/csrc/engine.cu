@@ -171,16 +171,17 @@ int sbv_launch_sha256(sbv_engine *e, size_t n, const uint8_t *d_msgs, const uint
     CU(e, cudaGetLastError());
     return 0;
 }
-// H2D of a caller buffer on the lane's stream: direct when pinned, else through the lane's pinned staging area at offset
+// H2D of a caller buffer on the lane's stream (or on st): direct when pinned, else through the lane's pinned staging area at offset
 // `stage_off` (the caller sized it and does not reuse it until the stream has drained).
-int sbv_lane_h2d(sbv_engine *e, Dev::Lane &ln, void *dst, const void *src, size_t bytes, size_t &stage_off) {
+int sbv_lane_h2d(sbv_engine *e, Dev::Lane &ln, void *dst, const void *src, size_t bytes, size_t &stage_off, cudaStream_t st) {
     if (bytes == 0) return 0;
+    if (!st) st = ln.stream;
     if (is_pinned(src)) {
-        CU(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ln.stream));
+        CU(e, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
     } else {
         if (stage_off + bytes > ln.h_pin_cap) return fail(e, SBV_ERR_NOMEM, "pinned staging area too small (%zu + %zu > %zu)", stage_off, bytes, ln.h_pin_cap);
         memcpy(ln.h_pin + stage_off, src, bytes);
-        CU(e, cudaMemcpyAsync(dst, ln.h_pin + stage_off, bytes, cudaMemcpyHostToDevice, ln.stream));
+        CU(e, cudaMemcpyAsync(dst, ln.h_pin + stage_off, bytes, cudaMemcpyHostToDevice, st));
         stage_off += (bytes + 255) & ~(size_t)255;
     }
     return 0;
@@ -309,32 +310,89 @@ int sync_lane(sbv_engine *e, int lane) {
     return 0;
 }
 
-// stages the five field arrays of items [lo, lo+cnt) on device d's lane and enqueues the verify pipeline: the KEYS go
-// first, so that the grouping and the table construction run while r, s and the digests are still being copied
-int stage_and_verify(sbv_engine *e, Dev &d, int lane, uint8_t curve, size_t lo, size_t cnt, const uint8_t *r, const uint8_t *s, const uint8_t *qx,
-                     const uint8_t *qy, const uint8_t *digest, uint8_t digest_len) {
+// One shard of a keys-per-item host-buffer call on device d's lane: what to verify and where it comes from.
+struct BatchSrc {
+    const uint8_t *r, *s, *qx, *qy;
+    const uint8_t *digest;      // fixed-width digests, or nullptr: the digests are SHA-256 of the messages below
+    uint8_t digest_len;
+    const uint8_t *msgs;
+    const uint64_t *msg_off;
+};
+
+// Stages items [lo, lo+cnt) and enqueues hashing (if asked for) and the verify pipeline; verdicts land in ln.d_ok (and the
+// digests in ln.d_dig) in ln.stream order.  The KEYS go first, so that the grouping and the table construction run while
+// the rest of the batch is still being copied.  A LARGE shard (>= 2 * chunk_items) then arrives in chunks on the lane's
+// second stream while the lane's first stream hashes and verifies the chunks that are already there: the call costs
+// max(upload, arithmetic) instead of their sum (C3: 1,048,576 requests of 256 B are 411 MB of upload and ~10 ms of kernels).
+// extra_pinned / so_out: the caller stages more arrays behind ours (the quorum columns) in the lane's pinned area.
+int stage_and_verify(sbv_engine *e, Dev &d, int lane, uint8_t curve, size_t lo, size_t cnt, const BatchSrc &b, size_t extra_pinned = 0,
+                     size_t *so_out = nullptr) {
     const size_t L = fbytes(curve);
+    const bool hashing = b.digest == nullptr;
+    const uint32_t dlen = hashing ? 32u : b.digest_len;
     Dev::Lane &ln = d.lanes[lane];
     CU(e, cudaSetDevice(d.ordinal));
-    int rc = sbv_lane_ensure(e, d, ln, cnt, cnt * (4 * L + digest_len + 1) + 8 * 256);
+    const uint64_t base = hashing ? b.msg_off[lo] : 0, bytes = hashing ? b.msg_off[lo + cnt] - base : 0;
+    int chunks = 1;
+    if (e->chunk_items > 0 && cnt >= 2 * (size_t)e->chunk_items) {
+        chunks = (int)(cnt / (size_t)e->chunk_items);
+        if (chunks > SBV_MAX_CHUNKS) chunks = SBV_MAX_CHUNKS;
+    }
+    const size_t per = (((cnt + chunks - 1) / chunks) + 255) & ~(size_t)255;   // items per chunk
+    int rc = sbv_lane_ensure(e, d, ln, cnt ? cnt : 1, cnt * (4 * L + dlen + 1) + bytes + (cnt + 1) * 8 + (size_t)(4 * chunks + 8) * 256 + extra_pinned);
     if (rc) return rc;
+    if (hashing && (rc = sbv_lane_ensure_msgs(e, ln, bytes + 16, cnt + 1))) return rc;
+    cudaStream_t up = ln.stream;   // the stream the rest of the batch is uploaded on
+    if (chunks > 1) {
+        if (!ln.stream2) {
+            CU(e, cudaStreamCreateWithFlags(&ln.stream2, cudaStreamNonBlocking));
+            CU(e, cudaEventCreateWithFlags(&ln.ev_a, cudaEventDisableTiming));
+            CU(e, cudaEventCreateWithFlags(&ln.ev_b, cudaEventDisableTiming));
+        }
+        for (int c = 0; c < chunks; c++)
+            if (!ln.ev_chunk[c]) CU(e, cudaEventCreateWithFlags(&ln.ev_chunk[c], cudaEventDisableTiming));
+        up = ln.stream2;
+    }
     size_t so = 0;
-    if ((rc = sbv_lane_h2d(e, ln, ln.d_qx, qx + lo * L, cnt * L, so))) return rc;
-    if ((rc = sbv_lane_h2d(e, ln, ln.d_qy, qy + lo * L, cnt * L, so))) return rc;
+    if ((rc = sbv_lane_h2d(e, ln, ln.d_qx, b.qx + lo * L, cnt * L, so))) return rc;
+    if ((rc = sbv_lane_h2d(e, ln, ln.d_qy, b.qy + lo * L, cnt * L, so))) return rc;
     VerifyLaunch vl;
     {
         std::lock_guard<std::mutex> lk(e->mu);
-        if ((rc = sbv_launch_verify_begin(e, d, curve, cnt, ln.d_qx, ln.d_qy, ln.stream, &vl))) return rc;
+        if ((rc = sbv_launch_verify_begin(e, d, curve, cnt, ln.d_qx, ln.d_qy, ln.stream, &vl, chunks))) return rc;
     }
-    rc = sbv_lane_h2d(e, ln, ln.d_r, r + lo * L, cnt * L, so);
-    if (!rc) rc = sbv_lane_h2d(e, ln, ln.d_s, s + lo * L, cnt * L, so);
-    if (!rc) rc = sbv_lane_h2d(e, ln, ln.d_dig, digest + lo * digest_len, cnt * digest_len, so);
-    std::lock_guard<std::mutex> lk(e->mu);
-    if (rc) {  // a fault between the halves: hand the scratch set back (the caller fail-stops anyway)
+    auto abandon = [&](int code) {  // a fault between the halves: hand the scratch set back (the caller fail-stops anyway)
+        std::lock_guard<std::mutex> lk(e->mu);
         if (vl.w) vl.w->open = false;
-        return rc;
+        return code;
+    };
+    for (int c = 0; c < chunks; c++) {
+        const size_t clo = (size_t)c * per < cnt ? (size_t)c * per : cnt, cn = cnt - clo < per ? cnt - clo : per;
+        const size_t g = lo + clo;   // first item of the chunk in the caller's arrays
+        if (hashing && cn) {
+            const uint64_t o = b.msg_off[g] - base, len = b.msg_off[g + cn] - b.msg_off[g];
+            rc = sbv_lane_h2d(e, ln, ln.d_msgs + o, b.msgs + b.msg_off[g], len, so, up);
+            if (!rc) rc = sbv_lane_h2d(e, ln, ln.d_off + clo, b.msg_off + g, (cn + 1) * 8, so, up);
+        } else if (cn) {
+            rc = sbv_lane_h2d(e, ln, ln.d_dig + clo * dlen, b.digest + g * dlen, cn * dlen, so, up);
+        }
+        if (!rc) rc = sbv_lane_h2d(e, ln, ln.d_r + clo * L, b.r + g * L, cn * L, so, up);
+        if (!rc) rc = sbv_lane_h2d(e, ln, ln.d_s + clo * L, b.s + g * L, cn * L, so, up);
+        if (rc) return abandon(rc);
+        if (chunks > 1) {
+            cudaError_t ce = cudaEventRecord(ln.ev_chunk[c], up);
+            if (ce == cudaSuccess) ce = cudaStreamWaitEvent(ln.stream, ln.ev_chunk[c], 0);
+            if (ce != cudaSuccess) return abandon(sbv_fail(e, SBV_ERR_CUDA, "chunk event: %s", cudaGetErrorString(ce)));
+        }
+        if (hashing && cn && (rc = sbv_launch_sha256(e, cn, ln.d_msgs, ln.d_off + clo, base, ln.d_dig + clo * 32, ln.d_perm + clo, ln.stream)))
+            return abandon(rc);
+        std::lock_guard<std::mutex> lk(e->mu);
+        if (chunks == 1) rc = sbv_launch_verify_finish(e, d, vl, ln.d_r, ln.d_s, ln.d_dig, dlen, ln.d_ok, ln.stream);
+        else rc = sbv_launch_verify_chunk(e, d, vl, c, clo, cn, c == chunks - 1, ln.d_r, ln.d_s, ln.d_dig, dlen, ln.d_ok, ln.stream);
+        if (rc) { if (vl.w) vl.w->open = false; return rc; }
     }
-    return sbv_launch_verify_finish(e, d, vl, ln.d_r, ln.d_s, ln.d_dig, digest_len, ln.d_ok, ln.stream);
+    if (so_out) *so_out = so;
+    return 0;
 }
 
 }  // namespace
@@ -353,6 +411,7 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
     e->group_max_keys = env_int("SBV_GROUP_MAX_KEYS", 8192);
     e->group_min_batch = env_int("SBV_GROUP_MIN_BATCH", 0);
     e->gsplit = env_int("SBV_GSPLIT", 1) != 0;
+    e->chunk_items = env_int("SBV_CHUNK_ITEMS", 131072);
     {
         // per-engine hash seed: an adversary who picks the keys of a batch cannot aim at the probe sequence
         uint64_t t = (uint64_t)(uintptr_t)e;
@@ -466,7 +525,7 @@ int sbv_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *r, c
     const int lane = guard.lane;
     if (G == 1) {
         Dev &d = e->devs[0];
-        int rc = stage_and_verify(e, d, lane, curve, 0, n, r, s, qx, qy, digest, digest_len);
+        int rc = stage_and_verify(e, d, lane, curve, 0, n, BatchSrc{r, s, qx, qy, digest, digest_len, nullptr, nullptr});
         if (rc) return rc;
         CU(e, cudaMemcpyAsync(ok, d.lanes[lane].d_ok, n, cudaMemcpyDeviceToHost, d.lanes[lane].stream));
         return sync_lane(e, lane);
@@ -474,7 +533,7 @@ int sbv_verify_batch(sbv_engine *e, uint8_t curve, size_t n, const uint8_t *r, c
     for (int g = 0; g < G; g++) {
         Shard sh = shard_of(n, g, G);
         if (sh.n == 0) continue;
-        int rc = stage_and_verify(e, e->devs[g], lane, curve, sh.lo, sh.n, r, s, qx, qy, digest, digest_len);
+        int rc = stage_and_verify(e, e->devs[g], lane, curve, sh.lo, sh.n, BatchSrc{r, s, qx, qy, digest, digest_len, nullptr, nullptr});
         if (rc) return rc;
     }
     int rc = gather_verdicts(e, n, lane, 0);
@@ -560,7 +619,7 @@ int sbv_verify_batch_ranked(sbv_engine *e, int channel, uint8_t curve, size_t n,
     const int lane = guard.lane;
     Dev &d = e->devs[0];
     Dev::Lane &ln = d.lanes[lane];
-    int rc = stage_and_verify(e, d, lane, curve, 0, n, r, s, qx, qy, digest, digest_len);
+    int rc = stage_and_verify(e, d, lane, curve, 0, n, BatchSrc{r, s, qx, qy, digest, digest_len, nullptr, nullptr});
     if (rc) return rc;
     const size_t wp = (n + 31) / 32;
     if ((rc = sbv_lane_ensure_aux(e, ln, wp * (size_t)e->nranks * 4))) return rc;

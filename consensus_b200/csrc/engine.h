@@ -16,6 +16,7 @@
 
 constexpr int SBV_LANES = 6;    // concurrent host-buffer calls per engine
 constexpr int SBV_SCRATCH = 8;  // scratch sets per device (> SBV_LANES + 1: a launch may be held open per lane)
+constexpr int SBV_MAX_CHUNKS = 32;  // a large host-buffer batch is uploaded and verified in at most this many chunks
 
 struct Dev {
     int ordinal = 0;
@@ -33,7 +34,7 @@ struct Dev {
         // key grouping
         uint32_t hsize = 0;
         uint32_t *htab = nullptr, *rep = nullptr, *keylist = nullptr, *klist = nullptr, *glist = nullptr;
-        uint32_t *zeroed = nullptr;  // one memset: counters[4] then kcnt[cap]
+        uint32_t *zeroed = nullptr;  // one memset: counters[4], kcnt[n], then counters[4] per chunk of a chunked launch
         int32_t *keyid = nullptr, *item_kid = nullptr;
         // per-key tables of the launch
         uint32_t *bases = nullptr, *hs = nullptr, *ztop = nullptr, *pref = nullptr, *ktab = nullptr;
@@ -67,6 +68,7 @@ struct Dev {
         // second stream of the call (mixed-curve batches run their two pipelines side by side)
         cudaStream_t stream2 = nullptr;
         cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+        cudaEvent_t ev_chunk[SBV_MAX_CHUNKS] = {};  // "chunk c has arrived" (recorded on stream2, the upload stream of a chunked call)
     } lanes[SBV_LANES];
     // generic scratch of the entry points that serialise on the engine lock
     uint8_t *d_scratch = nullptr;
@@ -93,6 +95,7 @@ struct sbv_engine {
     int group_threshold = 16;      // a key gets a table when it occurs at least this often in a batch (SBV_GROUP_THRESHOLD; 0 = never)
     int group_max_keys = 8192;     // table slots per launch (SBV_GROUP_MAX_KEYS)
     int group_min_batch = 0;       // launches smaller than this skip the grouping (SBV_GROUP_MIN_BATCH)
+    int chunk_items = 131072;      // host-buffer shards of >= 2x this many items are uploaded and verified in chunks (SBV_CHUNK_ITEMS; 0 = never)
     bool gsplit = true;            // u1*G in its own kernel beside the table construction (SBV_GSPLIT=0: inside the fixed-base kernel)
     uint32_t hash_seed = 0x9e3779b9u;
     bool profiling = false;
@@ -140,13 +143,19 @@ struct VerifyLaunch {
     size_t n = 0;
     uint8_t curve = 0;
     bool grouping = false;
+    int chunks = 1;   // > 1: the second half comes chunk by chunk (sbv_launch_verify_chunk)
 };
 
 // ---- pipeline.cu: the verify pipelines (device pointers in, verdict bytes out; enqueue only, no sync) ----
 // keys-per-item: k_prep, key grouping, per-key tables for repeated keys, fixed-base kernel + generic kernel for the rest
 int sbv_launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_qx,
                       const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
-int sbv_launch_verify_begin(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_qx, const uint8_t *d_qy, cudaStream_t st, VerifyLaunch *vl);
+int sbv_launch_verify_begin(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_qx, const uint8_t *d_qy, cudaStream_t st, VerifyLaunch *vl,
+                            int chunks = 1);
+// second half for items [lo, lo + cn) of a launch begun with chunks > 1 (the pointers are those of the WHOLE batch);
+// `last` closes the launch
+int sbv_launch_verify_chunk(sbv_engine *e, Dev &d, const VerifyLaunch &vl, int c, size_t lo, size_t cn, bool last, const uint8_t *d_r, const uint8_t *d_s,
+                            const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
 int sbv_launch_verify_finish(sbv_engine *e, Dev &d, const VerifyLaunch &vl, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_dig, uint32_t dlen,
                              uint8_t *d_ok, cudaStream_t st);
 // registered keys (sbv_set_keys)
@@ -166,7 +175,7 @@ int sbv_lane_ensure_aux(sbv_engine *e, Dev::Lane &ln, size_t bytes);
 // d_perm: n + 3072 words of scratch (may be null: no length sort)
 int sbv_launch_sha256(sbv_engine *e, size_t n, const uint8_t *d_msgs, const uint64_t *d_off, uint64_t base, uint8_t *d_digest, uint32_t *d_perm,
                       cudaStream_t st);
-int sbv_lane_h2d(sbv_engine *e, Dev::Lane &ln, void *dst, const void *src, size_t bytes, size_t &stage_off);
+int sbv_lane_h2d(sbv_engine *e, Dev::Lane &ln, void *dst, const void *src, size_t bytes, size_t &stage_off, cudaStream_t st = nullptr);
 int sbv_ensure_scratch(sbv_engine *e, Dev &d, size_t bytes);
 
 // A host-buffer call owns one lane on every device for its duration.  On every exit path — faults included — the

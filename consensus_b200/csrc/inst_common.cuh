@@ -29,11 +29,17 @@ cudaError_t op_prep(uint32_t n, const uint8_t *r, const uint8_t *s, const uint8_
 template <class C>
 cudaError_t op_group(uint32_t n, const uint8_t *qx, const uint8_t *qy, uint32_t seed, uint32_t hmask, uint32_t *htab, uint32_t *rep,
                      uint32_t *kcnt, uint32_t threshold, uint32_t max_keys, int32_t *keyid, uint32_t *keylist, int32_t *item_kid,
-                     uint32_t *klist, uint32_t *glist, uint32_t *counters, cudaStream_t st) {
+                     uint32_t *klist, uint32_t *glist, uint32_t *counters, int route, cudaStream_t st) {
     const unsigned blocks = (n + 255) / 256;
     k_kg_insert<C><<<blocks, 256, 0, st>>>(n, qx, qy, seed, hmask, htab, rep, kcnt);
     k_kg_assign<<<blocks, 256, 0, st>>>(n, rep, kcnt, threshold, max_keys, keyid, keylist, counters);
-    k_kg_route<<<blocks, 256, 0, st>>>(n, rep, keyid, item_kid, klist, glist, counters);
+    if (route) k_kg_route<<<blocks, 256, 0, st>>>(n, rep, keyid, item_kid, klist, glist, counters);
+    return cudaGetLastError();
+}
+
+[[maybe_unused]] static cudaError_t op_route(uint32_t n, const uint32_t *rep, const int32_t *keyid, int32_t *item_kid, uint32_t *klist, uint32_t *glist,
+                            uint32_t *counters, cudaStream_t st) {
+    k_kg_route<<<(n + 255) / 256, 256, 0, st>>>(n, rep, keyid, item_kid, klist, glist, counters);
     return cudaGetLastError();
 }
 

@@ -28,10 +28,14 @@ struct CurveOps {
     cudaError_t (*gtable_init)(uint32_t *gtab, cudaStream_t st);
     cudaError_t (*prep)(uint32_t n, const uint8_t *r, const uint8_t *s, const uint8_t *dig, uint32_t dlen, uint32_t *uw, uint8_t *flags,
                         cudaStream_t st);
-    // key grouping: insert + assign + route (three launches); buffers zeroed / 0xff-filled by the caller
+    // key grouping: insert + assign (+ route when `route`: three launches); buffers zeroed / 0xff-filled by the caller
     cudaError_t (*group)(uint32_t n, const uint8_t *qx, const uint8_t *qy, uint32_t seed, uint32_t hmask, uint32_t *htab, uint32_t *rep,
                          uint32_t *kcnt, uint32_t threshold, uint32_t max_keys, int32_t *keyid, uint32_t *keylist, int32_t *item_kid,
-                         uint32_t *klist, uint32_t *glist, uint32_t *counters, cudaStream_t st);
+                         uint32_t *klist, uint32_t *glist, uint32_t *counters, int route, cudaStream_t st);
+    // the routing step alone, for a range of items (chunked launches route chunk by chunk: rep / item_kid / klist / glist
+    // point at the chunk, the indices written to the lists are chunk-local, counters are the chunk's own)
+    cudaError_t (*route)(uint32_t n, const uint32_t *rep, const int32_t *keyid, int32_t *item_kid, uint32_t *klist, uint32_t *glist,
+                         uint32_t *counters, cudaStream_t st);
     // u1*G of every item into gacc[3N][n] (the half of the fixed-base verification that does not need the key tables)
     cudaError_t (*gpart)(uint32_t n, const uint32_t *uw, const uint32_t *gtab, uint32_t *gacc, cudaStream_t st);
     cudaError_t (*coz)(uint32_t n, const uint8_t *qx, const uint8_t *qy, const uint8_t *r, const uint32_t *uw, const uint8_t *flags,

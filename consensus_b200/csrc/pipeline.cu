@@ -54,7 +54,7 @@ int take_scratch(sbv_engine *e, Dev &d, const CurveOps &ops, const KtOps *kt, si
         {(void **)&w.rep, &c.rep, g ? n * 4 : 0, ni * 4},
         {(void **)&w.klist, &c.klist, g ? n * 4 : 0, ni * 4},
         {(void **)&w.glist, &c.glist, g ? n * 4 : 0, ni * 4},
-        {(void **)&w.zeroed, &c.zeroed, g ? (n + 4) * 4 : 0, (ni + 4) * 4},
+        {(void **)&w.zeroed, &c.zeroed, g ? (n + 4 + 4 * SBV_MAX_CHUNKS) * 4 : 0, (ni + 4 + 4 * SBV_MAX_CHUNKS) * 4},
         {(void **)&w.keyid, &c.keyid, g ? n * 4 : 0, ni * 4},
         {(void **)&w.item_kid, &c.item_kid, g ? n * 4 : 0, ni * 4},
         {(void **)&w.keylist, &c.keylist, t ? kcap * 4 : 0, kc * 4},
@@ -144,9 +144,10 @@ int sbv_init_gtables(sbv_engine *e, Dev &d) {
 //   begin : scratch set, key grouping on st, table construction on the set's side stream   (needs qx, qy)
 //   finish: k_prep, generic kernel on the second side stream, fixed-base kernel, join       (needs r, s, digest)
 int sbv_launch_verify_begin(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_qx, const uint8_t *d_qy, cudaStream_t st,
-                            VerifyLaunch *vl) {
+                            VerifyLaunch *vl, int chunks) {
     *vl = VerifyLaunch{};
     if (n == 0) return 0;
+    if (chunks < 1 || chunks > SBV_MAX_CHUNKS) return sbv_fail(e, SBV_ERR_ARG, "bad chunk count %d", chunks);
     const CurveOps &ops = sbv_ops(curve);
     const KtOps *kt = ops.kt5;
     const uint32_t nn = (uint32_t)n;
@@ -161,26 +162,88 @@ int sbv_launch_verify_begin(sbv_engine *e, Dev &d, uint8_t curve, size_t n, cons
     Dev::Scratch *w = nullptr;
     if (int rc = take_scratch(e, d, ops, grouping ? kt : nullptr, n, kcap, st, &w)) return rc;
     w->open = true;  // until sbv_launch_verify_finish records the set's `done` event
-    vl->w = w; vl->curve = curve; vl->n = n; vl->grouping = grouping; vl->d_qx = d_qx; vl->d_qy = d_qy;
+    vl->w = w; vl->curve = curve; vl->n = n; vl->grouping = grouping; vl->d_qx = d_qx; vl->d_qy = d_qy; vl->chunks = chunks;
     vl->ev = prof_take(e, d);
     if (vl->ev) CU(e, cudaEventRecord(vl->ev[0], st));
     if (!grouping) return 0;
     uint32_t *counters = w->zeroed, *kcnt = w->zeroed + 4;
     CU(e, cudaMemsetAsync(w->htab, 0xff, (size_t)w->hsize * 4, st));
-    CU(e, cudaMemsetAsync(w->zeroed, 0, (n + 4) * 4, st));
+    CU(e, cudaMemsetAsync(w->zeroed, 0, (n + 4 + (chunks > 1 ? 4 * chunks : 0)) * 4, st));
     CU(e, ops.group(nn, d_qx, d_qy, e->hash_seed, w->hsize - 1, w->htab, w->rep, kcnt, T, (uint32_t)kcap, w->keyid, w->keylist, w->item_kid, w->klist,
-                    w->glist, counters, st));
+                    w->glist, counters, chunks == 1, st));
     CU(e, cudaEventRecord(w->ev_group, st));
     CU(e, cudaStreamWaitEvent(w->s_tab, w->ev_group, 0));
     CU(e, kt->build(counters + 0, (uint32_t)kcap, w->keylist, d_qx, d_qy, w->bases, w->hs, w->ztop, w->pref, w->ktab, w->keyflags, w->s_tab));
     CU(e, cudaEventRecord(w->ev_tab, w->s_tab));
-    e->launches += 7;
+    e->launches += chunks == 1 ? 7 : 6;
+    return 0;
+}
+
+// One chunk of a chunked launch: the items [lo, lo + cn) are a batch of their own as far as the per-item arrays go (every one
+// of them is word-major with the batch size as its stride, so the chunk's slice is the contiguous block at `words per item *
+// lo`); what the chunks share is the grouping (hash table, rep, key ids) and the key tables.
+int sbv_launch_verify_chunk(sbv_engine *e, Dev &d, const VerifyLaunch &vl, int c, size_t lo, size_t cn, bool last, const uint8_t *d_r, const uint8_t *d_s,
+                            const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st) {
+    if (vl.n == 0) return 0;
+    Dev::Scratch *w = vl.w;
+    if (vl.chunks <= 1 || c < 0 || c >= vl.chunks || lo + cn > vl.n) return sbv_fail(e, SBV_ERR_ARG, "bad chunk");
+    const CurveOps &ops = sbv_ops(vl.curve);
+    const KtOps *kt = ops.kt5;
+    const size_t N = (size_t)ops.N, L = (size_t)ops.bytes;
+    const uint32_t nn = (uint32_t)cn;
+    const uint32_t *gtab = d.gtab[vl.curve];
+    cudaEvent_t *ev = c == 0 ? vl.ev : nullptr;  // the profile of a chunked launch is that of its first chunk
+    uint32_t *uw = w->uw + 2 * N * lo, *tscr = w->tscr + 12 * N * lo;
+    uint8_t *flags = w->flags + lo;
+    const uint8_t *r = d_r + lo * L;
+    if (cn) {
+        CU(e, ops.prep(nn, r, d_s + lo * L, d_dig + lo * dlen, dlen, uw, flags, st));
+        e->launches += 1;
+    }
+    if (ev) CU(e, cudaEventRecord(ev[1], st));
+    if (!vl.grouping) {
+        if (ev) { CU(e, cudaEventRecord(ev[4], st)); CU(e, cudaEventRecord(ev[2], st)); }
+        if (cn) {
+            CU(e, ops.coz(nn, vl.d_qx + lo * L, vl.d_qy + lo * L, r, uw, flags, gtab, tscr, d_ok + lo, nullptr, nullptr, st));
+            e->launches += 1;
+        }
+        if (ev) CU(e, cudaEventRecord(ev[3], st));
+    } else if (cn) {
+        uint32_t *cc = w->zeroed + 4 + vl.n + 4 * (size_t)c;   // this chunk's counters (zeroed by the first half)
+        uint32_t *klist = w->klist + lo, *glist = w->glist + lo;
+        CU(e, ops.route(nn, w->rep + lo, w->keyid, w->item_kid + lo, klist, glist, cc, st));
+        CU(e, cudaEventRecord(w->ev_prep, st));
+        CU(e, cudaStreamWaitEvent(w->s_gen, w->ev_prep, 0));
+        CU(e, ops.coz(nn, vl.d_qx + lo * L, vl.d_qy + lo * L, r, uw, flags, gtab, tscr, d_ok + lo, glist, cc + 2, w->s_gen));
+        CU(e, cudaEventRecord(w->ev_gen, w->s_gen));
+        const uint32_t *gacc = nullptr;
+        if (e->gsplit) {
+            uint32_t *ga = w->gacc + 3 * N * lo;
+            CU(e, ops.gpart(nn, uw, gtab, ga, st));
+            gacc = ga;
+            e->launches += 1;
+        }
+        if (ev) CU(e, cudaEventRecord(ev[4], st));
+        if (c == 0) CU(e, cudaStreamWaitEvent(st, w->ev_tab, 0));
+        if (ev) CU(e, cudaEventRecord(ev[2], st));
+        CU(e, kt->verify(0, 0, nn, nullptr, w->item_kid + lo, 0, w->keyflags, r, uw, flags, gtab, w->ktab, d_ok + lo, klist, cc + 1, gacc, st));
+        if (ev) CU(e, cudaEventRecord(ev[3], st));
+        CU(e, cudaStreamWaitEvent(st, w->ev_gen, 0));
+        e->launches += 3;
+    } else if (ev) {
+        CU(e, cudaEventRecord(ev[4], st)); CU(e, cudaEventRecord(ev[2], st)); CU(e, cudaEventRecord(ev[3], st));
+    }
+    if (last) {
+        CU(e, cudaEventRecord(w->done, st));
+        w->open = false;
+    }
     return 0;
 }
 
 int sbv_launch_verify_finish(sbv_engine *e, Dev &d, const VerifyLaunch &vl, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_dig,
                              uint32_t dlen, uint8_t *d_ok, cudaStream_t st) {
     if (vl.n == 0) return 0;
+    if (vl.chunks != 1) return sbv_fail(e, SBV_ERR_ARG, "chunked launch finished in one piece");
     const CurveOps &ops = sbv_ops(vl.curve);
     const KtOps *kt = ops.kt5;
     Dev::Scratch *w = vl.w;

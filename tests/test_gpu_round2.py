@@ -248,3 +248,72 @@ def test_multi_device_concurrent_callers():
         for t in ths: t.start()
         for t in ths: t.join()
     assert not errs, errs
+
+
+def _signed_requests(curve, n, K, seed, lo=40, hi=700):
+    msgs, off = corpus.make_requests(n, seed=seed, fixed_len=None, lo=lo, hi=hi)
+    d, kxy = corpus.make_keys(curve, K, seed=seed + 1)
+    L = 32 if curve == P256 else 48
+    key_idx = (np.arange(n) * 7 % K).astype(np.uint32)
+    dig = oracle.sha256_batch(msgs, off)
+    r, s = oracle.sign_batch(curve, d, key_idx, dig, corpus._blocks(seed + 2, n, L, b"k"))
+    qx, qy = np.ascontiguousarray(kxy[key_idx, :L]), np.ascontiguousarray(kxy[key_idx, L:])
+    msgs = msgs.copy()
+    for i in range(0, n, 5):
+        msgs[int(off[i]) + (i % int(off[i + 1] - off[i]))] ^= 1     # payload bit
+    s[::7, 9] ^= 2                                                   # signature bit
+    qx[::11] = qx[3]                                                 # another signer's key
+    return msgs, off, r, s, qx, qy
+
+
+@pytest.mark.parametrize("thr", [16, 0, 1])
+def test_chunked_upload_equals_oracle(thr):
+    """A shard of >= 2 x SBV_CHUNK_ITEMS items arrives and is verified chunk by chunk (shared grouping and key tables,
+    chunk-local routing): same verdicts and digests as the oracle, for a chunk size that does not divide the batch, with
+    grouping on, off, and with a table for every key — from pageable and from pinned caller memory."""
+    import torch
+    e = _engine(SBV_CHUNK_ITEMS=1000, SBV_GROUP_THRESHOLD=thr)
+    try:
+        for curve, n, K in [(P256, 7013, 41), (P384, 2300, 9), (P256, 2000, 2000)]:
+            msgs, off, r, s, qx, qy = _signed_requests(curve, n, K, seed=900 + n)
+            want_dig = oracle.sha256_batch(msgs, off)
+            want = oracle.verify_batch(curve, r, s, qx, qy, want_dig)
+            assert 0 < want.sum() < n
+            got, got_dig = e.hash_verify_batch(curve, msgs, off, r, s, qx, qy, want_digest=True)
+            assert np.array_equal(got_dig, want_dig)
+            assert np.array_equal(got, want), (curve, n, np.nonzero(got != want)[0][:10])
+            assert np.array_equal(e.verify_batch(curve, r, s, qx, qy, want_dig), want)
+            # pinned caller memory: the chunks are copied straight from the caller's buffers on the upload stream
+            pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+            assert np.array_equal(e.verify_batch(curve, pin(r), pin(s), pin(qx), pin(qy), pin(want_dig)), want)
+            assert np.array_equal(e.hash_verify_batch(curve, pin(msgs), pin(off), pin(r), pin(s), pin(qx), pin(qy)), want)
+        # back to a small (unchunked) call on the same engine and lanes
+        b = corpus.make_batch(P256, n=500, K=4, seed=77, corrupt_rate=5)
+        assert np.array_equal(e.verify_batch(P256, b["r"], b["s"], b["qx"], b["qy"], b["digest"]),
+                              oracle.verify_batch(P256, b["r"], b["s"], b["qx"], b["qy"], b["digest"]))
+    finally:
+        e.close()
+
+
+def test_chunked_upload_many_chunks_and_concurrent_callers():
+    """More chunks than SBV_MAX_CHUNKS would allow at the nominal size (clamped), from several caller threads at once."""
+    import threading
+    e = _engine(SBV_CHUNK_ITEMS=64)
+    try:
+        jobs = []
+        for t in range(3):
+            msgs, off, r, s, qx, qy = _signed_requests(P256, 5000 + 300 * t, 13 + t, seed=950 + t)
+            jobs.append((msgs, off, r, s, qx, qy, oracle.verify_batch(P256, r, s, qx, qy, oracle.sha256_batch(msgs, off))))
+        out = [None] * len(jobs)
+
+        def run(i):
+            m, o, r, s, qx, qy, _ = jobs[i]
+            for _ in range(3):
+                out[i] = e.hash_verify_batch(P256, m, o, r, s, qx, qy)
+        th = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        for i, j in enumerate(jobs):
+            assert np.array_equal(out[i], j[6]), i
+    finally:
+        e.close()
