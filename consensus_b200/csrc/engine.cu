@@ -321,7 +321,7 @@ struct BatchSrc {
 
 // Stages items [lo, lo+cnt) and enqueues hashing (if asked for) and the verify pipeline; verdicts land in ln.d_ok (and the
 // digests in ln.d_dig) in ln.stream order.  The KEYS go first, so that the grouping and the table construction run while
-// the rest of the batch is still being copied.  A LARGE shard (>= 2 * chunk_items) then arrives in chunks on the lane's
+// the rest of the batch is still being copied.  A LARGE shard (>= chunk_items) then arrives in chunks on the lane's
 // second stream while the lane's first stream hashes and verifies the chunks that are already there: the call costs
 // max(upload, arithmetic) instead of their sum (C3: 1,048,576 requests of 256 B are 411 MB of upload and ~10 ms of kernels).
 // extra_pinned / so_out: the caller stages more arrays behind ours (the quorum columns) in the lane's pinned area.
@@ -334,9 +334,8 @@ int stage_and_verify(sbv_engine *e, Dev &d, int lane, uint8_t curve, size_t lo, 
     CU(e, cudaSetDevice(d.ordinal));
     const uint64_t base = hashing ? b.msg_off[lo] : 0, bytes = hashing ? b.msg_off[lo + cnt] - base : 0;
     int chunks = 1;
-    if (e->chunk_items > 0 && cnt >= 2 * (size_t)e->chunk_items) {
-        chunks = (int)(cnt / (size_t)e->chunk_items);
-        if (chunks > SBV_MAX_CHUNKS) chunks = SBV_MAX_CHUNKS;
+    if (e->chunk_items > 0 && cnt >= (size_t)e->chunk_items) {  // at least two chunks, nominally chunk_items each
+        chunks = (int)std::min<size_t>(std::max<size_t>(cnt / (size_t)e->chunk_items, 2), SBV_MAX_CHUNKS);
     }
     const size_t per = (((cnt + chunks - 1) / chunks) + 255) & ~(size_t)255;   // items per chunk
     int rc = sbv_lane_ensure(e, d, ln, cnt ? cnt : 1, cnt * (4 * L + dlen + 1) + bytes + (cnt + 1) * 8 + (size_t)(4 * chunks + 8) * 256 + extra_pinned);
@@ -363,7 +362,7 @@ int stage_and_verify(sbv_engine *e, Dev &d, int lane, uint8_t curve, size_t lo, 
     }
     auto abandon = [&](int code) {  // a fault between the halves: hand the scratch set back (the caller fail-stops anyway)
         std::lock_guard<std::mutex> lk(e->mu);
-        if (vl.w) vl.w->open = false;
+        sbv_launch_verify_abort(vl, ln.stream);
         return code;
     };
     for (int c = 0; c < chunks; c++) {
@@ -389,7 +388,7 @@ int stage_and_verify(sbv_engine *e, Dev &d, int lane, uint8_t curve, size_t lo, 
         std::lock_guard<std::mutex> lk(e->mu);
         if (chunks == 1) rc = sbv_launch_verify_finish(e, d, vl, ln.d_r, ln.d_s, ln.d_dig, dlen, ln.d_ok, ln.stream);
         else rc = sbv_launch_verify_chunk(e, d, vl, c, clo, cn, c == chunks - 1, ln.d_r, ln.d_s, ln.d_dig, dlen, ln.d_ok, ln.stream);
-        if (rc) { if (vl.w) vl.w->open = false; return rc; }
+        if (rc) { sbv_launch_verify_abort(vl, ln.stream); return rc; }
     }
     if (so_out) *so_out = so;
     return 0;
@@ -411,7 +410,7 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
     e->group_max_keys = env_int("SBV_GROUP_MAX_KEYS", 8192);
     e->group_min_batch = env_int("SBV_GROUP_MIN_BATCH", 0);
     e->gsplit = env_int("SBV_GSPLIT", 1) != 0;
-    e->chunk_items = env_int("SBV_CHUNK_ITEMS", 131072);
+    e->chunk_items = env_int("SBV_CHUNK_ITEMS", 262144);
     {
         // per-engine hash seed: an adversary who picks the keys of a batch cannot aim at the probe sequence
         uint64_t t = (uint64_t)(uintptr_t)e;

@@ -95,7 +95,7 @@ struct sbv_engine {
     int group_threshold = 16;      // a key gets a table when it occurs at least this often in a batch (SBV_GROUP_THRESHOLD; 0 = never)
     int group_max_keys = 8192;     // table slots per launch (SBV_GROUP_MAX_KEYS)
     int group_min_batch = 0;       // launches smaller than this skip the grouping (SBV_GROUP_MIN_BATCH)
-    int chunk_items = 131072;      // host-buffer shards of >= 2x this many items are uploaded and verified in chunks (SBV_CHUNK_ITEMS; 0 = never)
+    int chunk_items = 262144;      // host-buffer shards of >= this many items are uploaded and verified in >= 2 chunks of nominally this size (SBV_CHUNK_ITEMS; 0 = never)
     bool gsplit = true;            // u1*G in its own kernel beside the table construction (SBV_GSPLIT=0: inside the fixed-base kernel)
     uint32_t hash_seed = 0x9e3779b9u;
     bool profiling = false;
@@ -152,6 +152,7 @@ int sbv_launch_verify(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint
                       const uint8_t *d_qy, const uint8_t *d_dig, uint32_t dlen, uint8_t *d_ok, cudaStream_t st);
 int sbv_launch_verify_begin(sbv_engine *e, Dev &d, uint8_t curve, size_t n, const uint8_t *d_qx, const uint8_t *d_qy, cudaStream_t st, VerifyLaunch *vl,
                             int chunks = 1);
+void sbv_launch_verify_abort(const VerifyLaunch &vl, cudaStream_t st);  // hand the scratch set back after a fault between the halves
 // second half for items [lo, lo + cn) of a launch begun with chunks > 1 (the pointers are those of the WHOLE batch);
 // `last` closes the launch
 int sbv_launch_verify_chunk(sbv_engine *e, Dev &d, const VerifyLaunch &vl, int c, size_t lo, size_t cn, bool last, const uint8_t *d_r, const uint8_t *d_s,

@@ -240,6 +240,16 @@ int sbv_launch_verify_chunk(sbv_engine *e, Dev &d, const VerifyLaunch &vl, int c
     return 0;
 }
 
+// A fault between the halves: the set goes back, but only behind whatever the first half left running on its side stream.
+void sbv_launch_verify_abort(const VerifyLaunch &vl, cudaStream_t st) {
+    Dev::Scratch *w = vl.w;
+    if (!w || !w->open) return;
+    if (vl.grouping) cudaStreamWaitEvent(st, w->ev_tab, 0);
+    cudaStreamWaitEvent(st, w->ev_gen, 0);   // a chunk's generic kernel (a never-recorded event is a no-op)
+    cudaEventRecord(w->done, st);
+    w->open = false;
+}
+
 int sbv_launch_verify_finish(sbv_engine *e, Dev &d, const VerifyLaunch &vl, const uint8_t *d_r, const uint8_t *d_s, const uint8_t *d_dig,
                              uint32_t dlen, uint8_t *d_ok, cudaStream_t st) {
     if (vl.n == 0) return 0;
