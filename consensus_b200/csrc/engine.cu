@@ -411,6 +411,8 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
     e->group_min_batch = env_int("SBV_GROUP_MIN_BATCH", 0);
     e->gsplit = env_int("SBV_GSPLIT", 1) != 0;
     e->chunk_items = env_int("SBV_CHUNK_ITEMS", 262144);
+    e->gather_hi = env_int("SBV_GATHER_PRIORITY", 0) != 0;
+    e->tab_hi = env_int("SBV_TAB_PRIORITY", 0) != 0;
     {
         // per-engine hash seed: an adversary who picks the keys of a batch cannot aim at the probe sequence
         uint64_t t = (uint64_t)(uintptr_t)e;
@@ -454,6 +456,11 @@ void sbv_destroy(sbv_engine *e) {
     }
     for (void *c : e->nccl_comms) if (c && g_nccl.comm_destroy) g_nccl.comm_destroy(c);
     for (void *c : e->rank_comms) if (c && g_nccl.comm_destroy) g_nccl.comm_destroy(c);
+    for (auto &hi : e->rank_hi) {
+        if (hi.st) cudaStreamDestroy(hi.st);
+        if (hi.in) cudaEventDestroy(hi.in);
+        if (hi.out) cudaEventDestroy(hi.out);
+    }
     for (Dev &d : e->devs) {
         cudaSetDevice(d.ordinal);
         void *ptrs[] = {d.gtab[0], d.gtab[1], d.d_scratch};
@@ -565,8 +572,17 @@ int sbv_comm_init_rank(sbv_engine *e, const uint8_t *id128, int nranks, int rank
     memcpy(id.internal, id128, 128);
     void *comm = nullptr;
     NC(e, g_nccl.comm_init_rank(&comm, nranks, id, rank));
+    sbv_engine::ChannelHi hi;
+    if (e->gather_hi) {
+        int lo_p = 0, hi_p = 0;
+        CU(e, cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+        CU(e, cudaStreamCreateWithPriority(&hi.st, cudaStreamNonBlocking, hi_p));
+        CU(e, cudaEventCreateWithFlags(&hi.in, cudaEventDisableTiming));
+        CU(e, cudaEventCreateWithFlags(&hi.out, cudaEventDisableTiming));
+    }
     std::lock_guard<std::mutex> lk(e->mu);
     e->rank_comms.push_back(comm);
+    e->rank_hi.push_back(hi);
     e->rank = rank;
     e->nranks = nranks;
     return (int)e->rank_comms.size() - 1;
@@ -584,12 +600,23 @@ int sbv_gather_verdicts_device(sbv_engine *e, int channel, const uint8_t *d_ok, 
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const size_t wp = (n + 31) / 32;
     uint32_t *mine = d_mask_all + wp * (size_t)e->rank;
-    k_pack_bits<<<(uint32_t)((n + 255) / 256), 256, 0, st>>>((uint32_t)n, d_ok, mine);
+    if (e->nranks > 1 && (channel < 0 || channel >= (int)e->rank_comms.size())) return fail(e, SBV_ERR_NCCL, "no such channel: call sbv_comm_init_rank first");
+    const bool fork = e->nranks > 1 && e->rank_hi[channel].st;
+    cudaStream_t gs = st;
+    if (fork) {  // the exchange runs on the channel's high-priority stream, between two events on the caller's stream
+        const sbv_engine::ChannelHi &hi = e->rank_hi[channel];
+        CU(e, cudaEventRecord(hi.in, st));
+        CU(e, cudaStreamWaitEvent(hi.st, hi.in, 0));
+        gs = hi.st;
+    }
+    k_pack_bits<<<(uint32_t)((n + 255) / 256), 256, 0, gs>>>((uint32_t)n, d_ok, mine);
     e->launches += 1;
     CU(e, cudaGetLastError());
-    if (e->nranks > 1) {
-        if (channel < 0 || channel >= (int)e->rank_comms.size()) return fail(e, SBV_ERR_NCCL, "no such channel: call sbv_comm_init_rank first");
-        NC(e, g_nccl.all_gather(mine, d_mask_all, wp, NCCL_UINT32, e->rank_comms[channel], st));
+    if (e->nranks > 1) NC(e, g_nccl.all_gather(mine, d_mask_all, wp, NCCL_UINT32, e->rank_comms[channel], gs));
+    if (fork) {
+        const sbv_engine::ChannelHi &hi = e->rank_hi[channel];
+        CU(e, cudaEventRecord(hi.out, gs));
+        CU(e, cudaStreamWaitEvent(st, hi.out, 0));
     }
     return SBV_OK;
 }

@@ -105,6 +105,12 @@ struct sbv_engine {
     // one-process-per-GPU deployments: this engine is rank `rank` of `nranks`.  One communicator per CHANNEL: the
     // collectives of a channel must be issued in the same order on every rank, so concurrent host threads take one each.
     std::vector<void *> rank_comms;
+    // per channel: a high-priority stream for the pack + all-gather of a step (fork / join with two events), so that the
+    // exchange is dispatched ahead of the pending blocks of other lanes' verification kernels (SBV_GATHER_PRIORITY)
+    struct ChannelHi { cudaStream_t st = nullptr; cudaEvent_t in = nullptr, out = nullptr; };
+    std::vector<ChannelHi> rank_hi;
+    bool gather_hi = false;
+    bool tab_hi = false;           // table-construction side streams at high priority (SBV_TAB_PRIORITY)
     int rank = 0, nranks = 1;
     // key registry
     uint64_t verification_seq = 0;

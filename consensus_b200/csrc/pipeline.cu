@@ -30,7 +30,13 @@ int take_scratch(sbv_engine *e, Dev &d, const CurveOps &ops, const KtOps *kt, si
         CU(e, cudaEventCreateWithFlags(&w.ev_prep, cudaEventDisableTiming));
         CU(e, cudaEventCreateWithFlags(&w.ev_tab, cudaEventDisableTiming));
         CU(e, cudaEventCreateWithFlags(&w.ev_gen, cudaEventDisableTiming));
-        CU(e, cudaStreamCreateWithFlags(&w.s_tab, cudaStreamNonBlocking));
+        if (e->tab_hi) {
+            int lo_p = 0, hi_p = 0;
+            CU(e, cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+            CU(e, cudaStreamCreateWithPriority(&w.s_tab, cudaStreamNonBlocking, hi_p));
+        } else {
+            CU(e, cudaStreamCreateWithFlags(&w.s_tab, cudaStreamNonBlocking));
+        }
         CU(e, cudaStreamCreateWithFlags(&w.s_gen, cudaStreamNonBlocking));
     }
     const size_t N = (size_t)ops.N;
