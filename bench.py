@@ -60,7 +60,8 @@ def load_peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    # (no power.draw: the power sensor read is the one query that can hold the GPU for milliseconds)
+    Q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
@@ -98,7 +99,7 @@ class ClockSampler:
         sm, mx, reasons, sm_all = [], [], set(), []
         for ts, row in self.rows:
             f = [x.strip() for x in row.split(",")]
-            if len(f) < 9:
+            if len(f) < 8:
                 continue
             try:
                 v, m = float(f[1]), float(f[2])
@@ -108,7 +109,7 @@ class ClockSampler:
             mx.append(m)
             if lo - 0.06 <= ts <= hi + 0.06:     # samples taken while the timed region ran
                 sm.append(v)
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                     if val.lower().startswith("active"):
                         reasons.add(name)
         use = sorted(sm or sm_all)
@@ -275,12 +276,20 @@ def main():
     sampler.mark()
     e0.record()
     fork_lanes()
+    step_done = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     for i in range(args.steps):
         device_step(args.warmup + i)
+        step_done[i].record(lanes[(args.warmup + i) % N_LANES])   # diagnostic only: when each step finished (timing_diag below)
     join_lanes()
     e1.record()
     torch.cuda.synchronize()
     sampler.mark()
+    done_ms = sorted(e0.elapsed_time(ev) for ev in step_done)
+    gaps = sorted(b - a for a, b in zip([0.0] + done_ms[:-1], done_ms))
+    timing_diag = {"step_completion_gap_ms": {"median": gaps[len(gaps) // 2], "p99": gaps[min(len(gaps) - 1, int(len(gaps) * 0.99))], "max": gaps[-1]},
+                   "first_step_done_ms": done_ms[0],
+                   "note": "gaps between consecutive step completions inside the timed region (all streams merged): a max far above the median is a "
+                           "stall of the whole device (e.g. a management query), not arithmetic"}
     launches = eng.kernel_launches - launches0
     barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -439,7 +448,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "verifies/s", "h2d_bytes_per_step": 160 * BATCH * world,
                 "d2h_bytes_per_step": (BATCH + (world * words * 4 if world > 1 else 0)) * world,
                 "callers": E2E_THREADS, "single_caller_value": e2e_single, "includes_gather": world > 1},
-        "step_latency_ms": step_latency_ms, "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "registered_keys": reg,
+        "step_latency_ms": step_latency_ms, "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "timing_diag": timing_diag, "registered_keys": reg,
     }
 
     if not args.no_extras:
@@ -591,7 +600,7 @@ def run_extras(eng, sbv, oracle, np, torch, dev, rank, world, local_rank, mad_pe
                                  "requests": n3, "e2e_s": t, "value": n3 / t, "unit": "requests/s",
                                  "through": "sbv_hash_verify_batch, pinned host buffers (H2D of 268 MB of requests + 128 B/item inside; keys first, "
                                             "then 4 chunks of 262,144 requests uploaded on a second stream while the previous chunk is hashed and verified)",
-                                 "chunks": 4, "verify_kernel_ms_per_chunk": v_ms / max(pairs, 1), "bit_exact_vs_oracle": bool(np.array_equal(ok3.numpy(), np.tile(want1, T16))),
+                                 "chunks": 4, "verify_kernel_ms_last_chunk": v_ms / max(pairs, 1), "bit_exact_vs_oracle": bool(np.array_equal(ok3.numpy(), np.tile(want1, T16))),
                                  "roofline_frac_canonical": n3 / t * MAC32_PER_VERIFY / mad_peak if mad_peak else None,
                                  "sha256_algorithmic_bytes": blocks * 64 + 32 * n3,
                                  "h2d_gbs": (n3 * (256 + 8 + 128)) / t / 1e9}

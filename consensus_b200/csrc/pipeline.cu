@@ -198,7 +198,8 @@ int sbv_launch_verify_chunk(sbv_engine *e, Dev &d, const VerifyLaunch &vl, int c
     const size_t N = (size_t)ops.N, L = (size_t)ops.bytes;
     const uint32_t nn = (uint32_t)cn;
     const uint32_t *gtab = d.gtab[vl.curve];
-    cudaEvent_t *ev = c == 0 ? vl.ev : nullptr;  // the profile of a chunked launch is that of its first chunk
+    cudaEvent_t *ev = last ? vl.ev : nullptr;  // the profile of a chunked launch is that of its last chunk (nothing of the first half overlaps it)
+    if (ev) CU(e, cudaEventRecord(ev[0], st));
     uint32_t *uw = w->uw + 2 * N * lo, *tscr = w->tscr + 12 * N * lo;
     uint8_t *flags = w->flags + lo;
     const uint8_t *r = d_r + lo * L;
