@@ -40,7 +40,7 @@ MAC32_PER_VERIFY_P384 = 902_880
 EXECUTED_MAC32_PER_VERIFY = 68 * (8 * 64 + 3 * 36) + (2 * 64 + 36)   # fixed-base path, P-256
 BYTES_PER_VERIFY = 161           # 160 B in + 1 B out
 N_COPIES = 16                    # rotating input copies: 16 x 10.5 MB > 126 MB L2
-N_LANES = 4
+N_LANES = int(os.environ.get("SBV_BENCH_LANES", "4"))   # CUDA streams the device-timed steps rotate over
 METRIC = "ECDSA-P256 verifies/sec at batch=64K"
 WORKLOAD = "C2: ECDSA-P256 batch verify, 65,536 synthetic sigs per GPU, 1,024 keys, 1/16 corrupted"
 
@@ -287,7 +287,7 @@ def main():
     done_ms = sorted(e0.elapsed_time(ev) for ev in step_done)
     gaps = sorted(b - a for a, b in zip([0.0] + done_ms[:-1], done_ms))
     timing_diag = {"step_completion_gap_ms": {"median": gaps[len(gaps) // 2], "p99": gaps[min(len(gaps) - 1, int(len(gaps) * 0.99))], "max": gaps[-1]},
-                   "first_step_done_ms": done_ms[0],
+                   "first_step_done_ms": done_ms[0], "step_done_ms": [round(x, 3) for x in done_ms[:64]],
                    "note": "gaps between consecutive step completions inside the timed region (all streams merged): a max far above the median is a "
                            "stall of the whole device (e.g. a management query), not arithmetic"}
     launches = eng.kernel_launches - launches0

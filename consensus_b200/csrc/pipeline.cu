@@ -25,19 +25,25 @@ int take_scratch(sbv_engine *e, Dev &d, const CurveOps &ops, const KtOps *kt, si
     Dev::Scratch &w = d.ws[idx];
     Dev::Scratch::Caps &c = w.caps;
     if (!w.done) {
-        CU(e, cudaEventCreateWithFlags(&w.done, cudaEventDisableTiming));
-        CU(e, cudaEventCreateWithFlags(&w.ev_group, cudaEventDisableTiming));
-        CU(e, cudaEventCreateWithFlags(&w.ev_prep, cudaEventDisableTiming));
-        CU(e, cudaEventCreateWithFlags(&w.ev_tab, cudaEventDisableTiming));
-        CU(e, cudaEventCreateWithFlags(&w.ev_gen, cudaEventDisableTiming));
-        if (e->tab_hi) {
-            int lo_p = 0, hi_p = 0;
-            CU(e, cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
-            CU(e, cudaStreamCreateWithPriority(&w.s_tab, cudaStreamNonBlocking, hi_p));
-        } else {
-            CU(e, cudaStreamCreateWithFlags(&w.s_tab, cudaStreamNonBlocking));
+        // The events and side streams of EVERY set are created now: a set first taken in the middle of a steady stream of
+        // launches would otherwise stop to create streams there (measured: 2 - 40 ms at the head of a timed region).
+        for (int j = 0; j < SBV_SCRATCH; j++) {
+            Dev::Scratch &x = d.ws[j];
+            if (x.done) continue;
+            CU(e, cudaEventCreateWithFlags(&x.done, cudaEventDisableTiming));
+            CU(e, cudaEventCreateWithFlags(&x.ev_group, cudaEventDisableTiming));
+            CU(e, cudaEventCreateWithFlags(&x.ev_prep, cudaEventDisableTiming));
+            CU(e, cudaEventCreateWithFlags(&x.ev_tab, cudaEventDisableTiming));
+            CU(e, cudaEventCreateWithFlags(&x.ev_gen, cudaEventDisableTiming));
+            if (e->tab_hi) {
+                int lo_p = 0, hi_p = 0;
+                CU(e, cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p));
+                CU(e, cudaStreamCreateWithPriority(&x.s_tab, cudaStreamNonBlocking, hi_p));
+            } else {
+                CU(e, cudaStreamCreateWithFlags(&x.s_tab, cudaStreamNonBlocking));
+            }
+            CU(e, cudaStreamCreateWithFlags(&x.s_gen, cudaStreamNonBlocking));
         }
-        CU(e, cudaStreamCreateWithFlags(&w.s_gen, cudaStreamNonBlocking));
     }
     const size_t N = (size_t)ops.N;
     uint32_t hsize = 1;
