@@ -276,17 +276,19 @@ def main():
     sampler.mark()
     e0.record()
     fork_lanes()
-    step_done = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    diag = os.environ.get("SBV_BENCH_DIAG", "1") != "0"
+    step_done = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps if diag else 0)]
     for i in range(args.steps):
         device_step(args.warmup + i)
-        step_done[i].record(lanes[(args.warmup + i) % N_LANES])   # diagnostic only: when each step finished (timing_diag below)
+        if diag:
+            step_done[i].record(lanes[(args.warmup + i) % N_LANES])   # diagnostic only: when each step finished (timing_diag below)
     join_lanes()
     e1.record()
     torch.cuda.synchronize()
     sampler.mark()
-    done_ms = sorted(e0.elapsed_time(ev) for ev in step_done)
+    done_ms = sorted(e0.elapsed_time(ev) for ev in step_done) or [0.0]
     gaps = sorted(b - a for a, b in zip([0.0] + done_ms[:-1], done_ms))
-    timing_diag = {"step_completion_gap_ms": {"median": gaps[len(gaps) // 2], "p99": gaps[min(len(gaps) - 1, int(len(gaps) * 0.99))], "max": gaps[-1]},
+    timing_diag = None if not diag else {"step_completion_gap_ms": {"median": gaps[len(gaps) // 2], "p99": gaps[min(len(gaps) - 1, int(len(gaps) * 0.99))], "max": gaps[-1]},
                    "first_step_done_ms": done_ms[0], "step_done_ms": [round(x, 3) for x in done_ms[:64]],
                    "note": "gaps between consecutive step completions inside the timed region (all streams merged): a max far above the median is a "
                            "stall of the whole device (e.g. a management query), not arithmetic"}

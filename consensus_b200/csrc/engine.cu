@@ -411,7 +411,7 @@ int sbv_create(const int *device_ordinals, int n_devices, sbv_engine **out) {
     e->group_min_batch = env_int("SBV_GROUP_MIN_BATCH", 0);
     e->gsplit = env_int("SBV_GSPLIT", 1) != 0;
     e->chunk_items = env_int("SBV_CHUNK_ITEMS", 262144);
-    e->gather_hi = env_int("SBV_GATHER_PRIORITY", 0) != 0;
+    e->gather_hi = env_int("SBV_GATHER_PRIORITY", 1) != 0;
     e->tab_hi = env_int("SBV_TAB_PRIORITY", 1) != 0;
     {
         // per-engine hash seed: an adversary who picks the keys of a batch cannot aim at the probe sequence

@@ -109,7 +109,7 @@ struct sbv_engine {
     // exchange is dispatched ahead of the pending blocks of other lanes' verification kernels (SBV_GATHER_PRIORITY)
     struct ChannelHi { cudaStream_t st = nullptr; cudaEvent_t in = nullptr, out = nullptr; };
     std::vector<ChannelHi> rank_hi;
-    bool gather_hi = false;
+    bool gather_hi = true;
     bool tab_hi = true;            // table-construction side streams at high priority: their few, latency-bound blocks are dispatched ahead of
                                    // the pending blocks of other launches' verification kernels (SBV_TAB_PRIORITY=0: e2e 72.9 -> 76 M/s with it)
     int rank = 0, nranks = 1;
