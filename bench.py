@@ -276,7 +276,7 @@ def main():
     sampler.mark()
     e0.record()
     fork_lanes()
-    diag = os.environ.get("SBV_BENCH_DIAG", "1") != "0"
+    diag = os.environ.get("SBV_BENCH_DIAG", "0") != "0"   # per-step completion events cost 4-5 % of the throughput (profiles/r02_variants.md): off by default
     step_done = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps if diag else 0)]
     for i in range(args.steps):
         device_step(args.warmup + i)
