@@ -31,8 +31,9 @@
  *    (r/s)Q must not be infinity; accept iff R.x mod n == r.  No low-S rule.
  *  - Thread-safe and re-entrant: the CUDA device is set explicitly per call, so calls may come from any
  *    OS thread (cgo).  Every host-buffer entry point owns a lane (stream, device buffers, pinned staging) for
- *    the duration of the call — four calls proceed concurrently and overlap their copies and kernels; a
- *    fifth waits.  On every return path, faults included, the lane has been drained: no copy into or out of
+ *    the duration of the call — six calls proceed concurrently and overlap their copies and kernels; a
+ *    seventh waits.  A shard of >= 262,144 items (SBV_CHUNK_ITEMS) is uploaded in chunks on a second stream while
+ *    the chunks that have arrived are hashed and verified.  On every return path, faults included, the lane has been drained: no copy into or out of
  *    the caller's buffers is in flight after the call returns, and on a fault the output arrays are untouched
  *    or partially written but never read as verdicts (the caller fail-stops).
  *  - Keys that repeat inside a keys-per-item batch are detected on the device and verified against a per-key
