@@ -1,13 +1,13 @@
 #!/bin/bash
 # N-GPU visit: the driver's own launch of bench.py at N ranks, the same without the high-priority exchange stream (A/B), and
-# N=1 on the same box.   usage: gpu_r2_multi.sh N [steps] [tests]
+# N=1 on the same box.   usage: gpu_r2_multi.sh N [steps] [tests 0/1] [A/B 0/1]
 N=${1:-2}
 STEPS=${2:-20}
 mkdir -p gpurun_out
 nvidia-smi -L | head -8
 if [ "${3:-0}" = "1" ]; then timeout 300 python -m pytest tests/test_gpu_parity.py tests/test_gpu_round2.py -q -k "multi_device" 2>&1 | tail -4; fi
 timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps $STEPS --warmup 5 > gpurun_out/m_bench_n$N.json 2> gpurun_out/m_bench_n$N.err; tail -5 gpurun_out/m_bench_n$N.err; cut -c1-300 gpurun_out/m_bench_n$N.json
-SBV_GATHER_PRIORITY=0 timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps $STEPS --warmup 5 --no-extras --no-cpu-baseline > gpurun_out/m_bench_n${N}_plain.json 2> gpurun_out/m_bench_n${N}_plain.err
+if [ "${4:-0}" = "1" ]; then SBV_GATHER_PRIORITY=0 timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps $STEPS --warmup 5 --no-extras --no-cpu-baseline > gpurun_out/m_bench_n${N}_plain.json 2> gpurun_out/m_bench_n${N}_plain.err; fi
 timeout 240 python bench.py --gpus 1 --steps $STEPS --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/m_bench_n1_of$N.json 2>/dev/null
 python - <<PY
 import json
