@@ -3,7 +3,7 @@
 
 A "step" is one pass of the hot path over one 65,536-signature batch PER GPU (batches shard embarrassingly, so per-GPU
 work is fixed as N grows: weak scaling); with N > 1 every step ends with the all-gather of the packed verdict bitmask
-over NCCL, issued by the engine itself (sbv_gather_verdicts_device: k_pack_bits + ncclAllGather on the step's stream) —
+over NCCL, issued by the engine itself (sbv_gather_verdicts_device: k_pack_bits + ncclAllGather, ordered behind the step on its stream) —
 the only exchange the path has.  No PyTorch kernel runs inside a step.
 
   value      device-timed, inputs already resident in HBM (16 rotating copies = 168 MB > L2), steps rotating over 4 streams
@@ -441,7 +441,7 @@ def main():
     cfg = base_config(world)
     cfg.update({"l2": f"{N_COPIES} rotating input copies (168 MB > 126 MB L2)",
                 "pipelining": f"consecutive steps rotate over {N_LANES} CUDA streams; unpipelined step latency in step_latency_ms",
-                "exchange": "engine-side k_pack_bits + ncclAllGather of the packed verdict bitmask per step, on the step's stream" if world > 1 else "none (1 GPU)",
+                "exchange": "engine-side k_pack_bits + ncclAllGather of the packed verdict bitmask per step, ordered behind the step on its stream (run on the channel's high-priority stream)" if world > 1 else "none (1 GPU)",
                 "key_grouping": "on (threshold 16): per-key fixed-base tables rebuilt inside every step"})
     line = {
         "metric": METRIC, "value": value, "unit": "verifies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
