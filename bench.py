@@ -46,7 +46,9 @@ WORKLOAD = "C2: ECDSA-P256 batch verify, 65,536 synthetic sigs per GPU, 1,024 ke
 
 
 def base_config(world):
-    return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "keys": KEYS, "seed": "1 + 1000*rank", "sharding": f"batch-parallel x{world}"}
+    """The workload — the same dict, key for key, in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "batch_per_gpu": BATCH, "keys": KEYS, "seed": "1 + 1000*rank", "sharding": f"batch-parallel x{world}",
+            "l2": f"GPU arm: {N_COPIES} rotating input copies per rank (168 MB > 126 MB L2), no flush needed; CPU arm: the rank-0 batch (10.5 MB) every step"}
 
 
 def load_peaks():
@@ -439,14 +441,14 @@ def main():
             pass
 
     cfg = base_config(world)
-    cfg.update({"l2": f"{N_COPIES} rotating input copies (168 MB > 126 MB L2)",
+    execution = dict({         # how THIS arm runs the workload (kept out of `config` so that both arms' configs are identical)
                 "pipelining": f"consecutive steps rotate over {N_LANES} CUDA streams; unpipelined step latency in step_latency_ms",
                 "exchange": "engine-side k_pack_bits + ncclAllGather of the packed verdict bitmask per step, ordered behind the step on its stream (run on the channel's high-priority stream)" if world > 1 else "none (1 GPU)",
                 "key_grouping": "on (threshold 16): per-key fixed-base tables rebuilt inside every step"})
     line = {
         "metric": METRIC, "value": value, "unit": "verifies/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u32 limbs (integer)", "data": "synthetic", "config": cfg,
+        "dtype": "u32 limbs (integer)", "data": "synthetic", "config": cfg, "execution": execution,
         "e2e": {"value": e2e_value, "unit": "verifies/s", "h2d_bytes_per_step": 160 * BATCH * world,
                 "d2h_bytes_per_step": (BATCH + (world * words * 4 if world > 1 else 0)) * world,
                 "callers": E2E_THREADS, "single_caller_value": e2e_single, "includes_gather": world > 1},
