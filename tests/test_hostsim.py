@@ -161,3 +161,23 @@ def test_verify_grouped_p384(hs):
     got, stats = _verify(hs, 1, b, grouped=(4, 16))
     assert np.array_equal(got, want)
     assert int(stats[1]) > 0
+
+
+@pytest.mark.parametrize("curve,n,K,thr,chunk", [(0, 250, 8, 4, 96), (0, 250, 8, 3, 37), (1, 60, 3, 4, 25)])
+def test_verify_chunked_second_half(hs, curve, n, K, thr, chunk):
+    """The second half of the pipeline run chunk by chunk (what a chunked host-buffer call enqueues, csrc/pipeline.cu:
+    sbv_launch_verify_chunk): shared grouping and key tables, per-chunk routing with chunk-local indices, every per-item
+    array addressed as the contiguous slice of the chunk — same verdicts and the same split between the two paths as
+    the one-piece launch, for chunk sizes that do not divide the batch, with and without the split u1*G kernel."""
+    cv = oracle.P256 if curve == 0 else oracle.P384
+    b = corpus.make_batch(cv, n=n, K=K, seed=25 + chunk, corrupt_rate=3)
+    want = oracle.verify_batch(cv, b["r"], b["s"], b["qx"], b["qy"], b["digest"])
+    whole, st_whole = _verify(hs, curve, b, grouped=(thr, 64))
+    ok = np.full(n, 7, np.uint8)
+    f = [np.ascontiguousarray(b[k]) for k in ("r", "s", "qx", "qy", "digest")]
+    stats = np.zeros(3, np.uint32)
+    assert hs.hs_verify_chunked(C.c_int(curve), C.c_size_t(n), *map(_p8, f), C.c_uint32(f[4].size // n), C.c_uint32(thr), C.c_uint32(64),
+                                C.c_uint32(chunk), _p8(ok), stats.ctypes.data_as(C.POINTER(C.c_uint32))) == 0
+    assert np.array_equal(ok, want)
+    assert np.array_equal(whole, want)
+    assert list(stats) == list(st_whole) and int(stats[1]) > 0

@@ -85,21 +85,22 @@ static void verify_coz_t(uint32_t n, const uint8_t *r, const uint8_t *s, const u
 // grouped path: k_prep, key grouping, table construction, k_verify_kt for repeated keys + k_verify_coz for the rest
 template <class C, int W>
 static void verify_grouped_t(uint32_t n, const uint8_t *r, const uint8_t *s, const uint8_t *qx, const uint8_t *qy, const uint8_t *dig,
-                             uint32_t dlen, const uint4 *gtab, uint32_t threshold, uint32_t max_keys, uint8_t *ok, uint32_t *stats) {
+                             uint32_t dlen, const uint4 *gtab, uint32_t threshold, uint32_t max_keys, uint8_t *ok, uint32_t *stats,
+                             uint32_t chunk = 0) {
     constexpr int N = C::N, S = 8;
     using KS = KtSizes<C, W>;
     using KT = KeyTab<32 * N, W>;
     std::vector<uint32_t> uw((size_t)2 * N * n);
     std::vector<uint8_t> flags(n);
     std::vector<uint32_t> tscr((size_t)12 * N * n);
-    run_grid(((n + S - 1) / S + 127) / 128, 128, [&] { k_prep<C, S>(n, r, s, dig, dlen, uw.data(), flags.data()); });
+    if (!chunk) run_grid(((n + S - 1) / S + 127) / 128, 128, [&] { k_prep<C, S>(n, r, s, dig, dlen, uw.data(), flags.data()); });
     uint32_t hsize = 1;
     while (hsize < 2 * n) hsize <<= 1;
     std::vector<uint32_t> htab(hsize, KG_EMPTY), rep(n), kcnt(n, 0), keylist(max_keys ? max_keys : 1), klist(n), glist(n), counters(4, 0);
     std::vector<int32_t> keyid(n), item_kid(n);
     run_grid((n + 255) / 256, 256, [&] { k_kg_insert<C>(n, qx, qy, 0x1234567u, hsize - 1, htab.data(), rep.data(), kcnt.data()); });
     run_grid((n + 255) / 256, 256, [&] { k_kg_assign(n, rep.data(), kcnt.data(), threshold, max_keys, keyid.data(), keylist.data(), counters.data()); });
-    run_grid((n + 255) / 256, 256, [&] { k_kg_route(n, rep.data(), keyid.data(), item_kid.data(), klist.data(), glist.data(), counters.data()); });
+    if (!chunk) run_grid((n + 255) / 256, 256, [&] { k_kg_route(n, rep.data(), keyid.data(), item_kid.data(), klist.data(), glist.data(), counters.data()); });
     const size_t cap = max_keys ? max_keys : 1;
     std::vector<uint32_t> bases(KS::bases_words(cap)), hs(KS::hs_words(cap)), ztop(KS::ztop_words(cap)), pref(KS::ztop_words(cap)), ktab(KS::ktab_words(cap));
     std::vector<uint8_t> kflags(cap, 0);
@@ -109,6 +110,31 @@ static void verify_grouped_t(uint32_t n, const uint8_t *r, const uint8_t *s, con
     run_grid((unsigned)((cap * KT::NWIN + 63) / 64), 64, [&] { k_kt_final<C, W>(counters.data(), (uint32_t)cap, bases.data(), kflags.data(), hs.data(), ztop.data(), ktab.data()); });
     const bool gsplit = (threshold & 1) == 0;  // exercise both forms: even thresholds take the split u1*G path
     std::vector<uint32_t> gacc((size_t)3 * N * n);
+    if (chunk) {
+        // The second half chunk by chunk, as sbv_launch_verify_chunk (csrc/pipeline.cu) enqueues it: the items [lo, lo + cn) are a
+        // batch of their own for every per-item array (word-major, stride = the chunk's size, base = words per item * lo); the
+        // grouping (rep, keyid) and the key tables are shared; routing is per chunk, chunk-local indices, the chunk's own counters.
+        const size_t L = C::BYTES;
+        uint32_t kt_total = 0, gen_total = 0;
+        for (uint32_t lo = 0; lo < n; lo += chunk) {
+            const uint32_t cn = n - lo < chunk ? n - lo : chunk;
+            std::vector<uint32_t> cc(4, 0);
+            uint32_t *uwc = uw.data() + (size_t)2 * N * lo, *tsc = tscr.data() + (size_t)12 * N * lo, *gac = gacc.data() + (size_t)3 * N * lo;
+            uint8_t *flc = flags.data() + lo;
+            const uint8_t *rc = r + lo * L;
+            run_grid(((cn + S - 1) / S + 127) / 128, 128, [&] { k_prep<C, S>(cn, rc, s + lo * L, dig + (size_t)lo * dlen, dlen, uwc, flc); });
+            run_grid((cn + 255) / 256, 256, [&] { k_kg_route(cn, rep.data() + lo, keyid.data(), item_kid.data() + lo, klist.data() + lo, glist.data() + lo, cc.data()); });
+            run_grid((cn + 63) / 64, 64, [&] { k_verify_coz<C, 64, 1>(cn, qx + lo * L, qy + lo * L, rc, uwc, flc, gtab, tsc, ok + lo, glist.data() + lo, cc.data() + 2); });
+            if (gsplit) run_grid((cn + 63) / 64, 64, [&] { k_gpart<C, 64, 1>(cn, uwc, gtab, gac); });
+            run_grid((cn + 63) / 64, 64, [&] {
+                k_verify_kt<C, W, 64, 1, false, false>(cn, nullptr, item_kid.data() + lo, 0, kflags.data(), rc, uwc, flc, gtab,
+                                                reinterpret_cast<const uint4 *>(ktab.data()), ok + lo, klist.data() + lo, cc.data() + 1, gsplit ? gac : nullptr);
+            });
+            kt_total += cc[1]; gen_total += cc[2];
+        }
+        if (stats) { stats[0] = counters[0]; stats[1] = kt_total; stats[2] = gen_total; }
+        return;
+    }
     if (gsplit) run_grid((n + 63) / 64, 64, [&] { k_gpart<C, 64, 1>(n, uw.data(), gtab, gacc.data()); });
     run_grid((n + 63) / 64, 64, [&] {
         k_verify_kt<C, W, 64, 1, false, false>(n, nullptr, item_kid.data(), 0, kflags.data(), r, uw.data(), flags.data(), gtab,
@@ -131,6 +157,14 @@ static const uint4 *gtab_for(int idx) {
         build_comb_host<C>(g.data());
     }
     return reinterpret_cast<const uint4 *>(g.data());
+}
+
+// the same with the second half run chunk by chunk (chunk = items per chunk), as a chunked host-buffer call does
+extern "C" int hs_verify_chunked(int curve, size_t n, const uint8_t *r, const uint8_t *s, const uint8_t *qx, const uint8_t *qy, const uint8_t *dig,
+                      uint32_t dlen, uint32_t threshold, uint32_t max_keys, uint32_t chunk, uint8_t *ok, uint32_t *stats) {
+    if (curve == 0) verify_grouped_t<P256, 5>((uint32_t)n, r, s, qx, qy, dig, dlen, gtab_for<P256>(0), threshold, max_keys, ok, stats, chunk);
+    else verify_grouped_t<P384, 5>((uint32_t)n, r, s, qx, qy, dig, dlen, gtab_for<P384>(1), threshold, max_keys, ok, stats, chunk);
+    return 0;
 }
 
 extern "C" int hs_verify(int curve, size_t n, const uint8_t *r, const uint8_t *s, const uint8_t *qx, const uint8_t *qy, const uint8_t *dig, uint32_t dlen,
