@@ -181,3 +181,45 @@ def test_verify_chunked_second_half(hs, curve, n, K, thr, chunk):
     assert np.array_equal(ok, want)
     assert np.array_equal(whole, want)
     assert list(stats) == list(st_whole) and int(stats[1]) > 0
+
+
+def _crafted(curve, cases):
+    """(u1, u2, k) -> a signature on Q = k*G whose verification computes exactly u1*G + u2*Q (s = r/u2, e = u1*s):
+    places exceptional points (doubling, P + (-P), infinity in the middle or at the end) inside the scalar multiplication."""
+    c = ref.CURVES[curve]
+    L = c.size
+    rows = []
+    for u1, u2, k in cases:
+        Q = ref.scalar_mult(c, k % c.n, (c.gx, c.gy))
+        R = ref._add(c, ref.scalar_mult(c, u1 % c.n, (c.gx, c.gy)), ref.scalar_mult(c, u2 % c.n, Q))
+        if u2 % c.n == 0:
+            continue
+        r = 1 if R is None else R[0] % c.n
+        if r == 0:
+            continue
+        s = r * pow(u2, -1, c.n) % c.n
+        rows.append((r, s, Q[0], Q[1], u1 * s % c.n))
+    f = lambda j: np.stack([np.frombuffer(int(row[j]).to_bytes(L, "big"), np.uint8) for row in rows])
+    return {"r": f(0), "s": f(1), "qx": f(2), "qy": f(3), "digest": f(4)}
+
+
+@pytest.mark.parametrize("curve,thr", [(0, 1), (0, 2), (1, 2)])
+def test_exceptional_points_on_the_fixed_base_path(hs, curve, thr):
+    """Every key gets a table (threshold 1 / 2: with the u1*G half inside the fixed-base kernel and in k_gpart) and the
+    scalars are chosen so that the running sum meets the next table entry (doubling inside a mixed addition), its
+    negative (infinity in the middle), or ends at infinity (must reject)."""
+    c = ref.CURVES[curve]
+    n = c.n
+    ks = [1, 2, 3, n - 1, 5, 2**8 + 1] if curve == 0 else [1, 3, n - 2]
+    cases = []
+    for k in ks:
+        for u1, u2 in [(1, 1), (k, 1), (n - k, 1), (k, n - 1), (2, n - 1), (1, 2), (7, 3), (2**255, 2**255), (n - 1, n - 1), (k * 5 % n, 5),
+                       (n - (k * 5 % n), 5), (k * 16 % n, 16), (n - (k * 16 % n), 16), (k * 33 % n, 33), (2**64, 2**64), (16, 1), (1, 16),
+                       (0, 1), (0, 77), ((k << 5) % n, 32), (n - ((k << 5) % n), 32)]:
+            cases.append((u1, u2, k))
+    b = _crafted(curve, cases)
+    want = oracle.verify_batch(curve, b["r"], b["s"], b["qx"], b["qy"], b["digest"])
+    assert 0 < int(want.sum()) < want.size
+    got, stats = _verify(hs, curve, b, grouped=(thr, 64))
+    assert int(stats[2]) == 0                                   # nothing on the generic path
+    assert np.array_equal(got, want), np.nonzero(got != want)[0][:10]
