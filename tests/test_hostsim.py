@@ -223,3 +223,47 @@ def test_exceptional_points_on_the_fixed_base_path(hs, curve, thr):
     got, stats = _verify(hs, curve, b, grouped=(thr, 64))
     assert int(stats[2]) == 0                                   # nothing on the generic path
     assert np.array_equal(got, want), np.nonzero(got != want)[0][:10]
+
+
+def _tables(hs, curve, w8, kxy, four):
+    L = 32 if curve == 0 else 48
+    n = kxy.shape[0]
+    qx, qy = np.ascontiguousarray(kxy[:, :L]), np.ascontiguousarray(kxy[:, L:])
+    hs.hs_ktab_words.restype = C.c_size_t
+    words = hs.hs_ktab_words(C.c_int(curve), C.c_int(w8), C.c_size_t(n))
+    kt, fl = np.zeros(words, np.uint32), np.zeros(n, np.uint8)
+    assert hs.hs_tables(C.c_int(curve), C.c_int(w8), C.c_size_t(n), _p8(qx), _p8(qy), C.c_int(four), kt.ctypes.data_as(C.POINTER(C.c_uint32)), _p8(fl)) == 0
+    return kt, fl
+
+
+@pytest.mark.parametrize("curve,w8,nkeys", [(0, 0, 6), (0, 1, 3), (1, 0, 3)])
+def test_four_lane_doubling_chain_in_lockstep(hs, curve, w8, nkeys):
+    """k_kt_bases4 — four lanes per key, the independent multiplications of a doubling on different lanes, quad shuffles —
+    simulated with one OS thread per lane meeting at every shuffle: the tables it leads to are bit-identical to those of the
+    one-thread-per-key kernel, the validity flags too (an off-curve key and a coordinate >= p among the keys), and every
+    entry of a table is e * 2^(W*w) * Q in affine Montgomery form."""
+    cv = oracle.P256 if curve == 0 else oracle.P384
+    c = ref.CURVES[cv]
+    L, N, W = c.size, c.size // 4, 8 if w8 else 5
+    d, kxy = corpus.make_keys(cv, nkeys, seed=3 + curve)
+    kxy = kxy.copy()
+    kxy[1, L + 8] ^= 1                                            # off the curve
+    if nkeys > 3:
+        kxy[4, :L] = np.frombuffer(int(c.p + 2).to_bytes(L, "big"), np.uint8)   # x >= p
+    a, fa = _tables(hs, curve, w8, kxy, four=0)
+    b, fb = _tables(hs, curve, w8, kxy, four=1)
+    assert fa.tolist() == fb.tolist() and fa[0] == 1 and fa[1] == 0 and (nkeys <= 3 or fa[4] == 0)
+    assert np.array_equal(a, b)
+    # key 0 against Python integers
+    nwin = (8 * L + 1 + W - 1) // W
+    ent = 1 << (W - 1)
+    tab = b[: nwin * ent * 2 * N].reshape(nwin, ent, 2, N)
+    Q = (int.from_bytes(kxy[0, :L].tobytes(), "big"), int.from_bytes(kxy[0, L:].tobytes(), "big"))
+    Rm = 1 << (8 * L)
+    val = lambda w: sum(int(x) << (32 * i) for i, x in enumerate(w))
+    for win in sorted({0, 1, nwin // 2, nwin - 1}):
+        for e in (1, 2, 3, ent - 1, ent):
+            if win == nwin - 1 and (e << (W * win)) >= c.n:
+                continue
+            P = ref.scalar_mult(c, (e << (W * win)) % c.n, Q)
+            assert val(tab[win, e - 1, 0]) == P[0] * Rm % c.p and val(tab[win, e - 1, 1]) == P[1] * Rm % c.p, (win, e)

@@ -5,10 +5,12 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <thread>
 #include <vector>
 
 #include "../../consensus_b200/csrc/hostsim.h"
 thread_local hostsim_dim3 threadIdx, blockIdx, blockDim, gridDim;
+thread_local hostsim_warp *hostsim_ctx = nullptr;
 namespace sbv { uint32_t tab[1 << 18]; }
 #include "../../consensus_b200/csrc/debug_ops.cuh"
 #include "../../consensus_b200/csrc/keygroup.cuh"
@@ -64,6 +66,57 @@ extern "C" int hs_debug_op(int curve, int op, size_t n, const uint32_t *a, const
         if (curve == 0) debug_op_item<P256>(op, (uint32_t)i, a, b, out);
         else debug_op_item<P384>(op, (uint32_t)i, a, b, out);
     }
+    return 0;
+}
+
+// LOCKSTEP form for warp-cooperative kernels: the 32 lanes of a warp are 32 OS threads that meet at every shuffle / ballot
+// (hostsim.h); warps run one after the other.
+template <class F>
+static void run_grid_lockstep(unsigned blocks, unsigned threads, F &&body) {
+    for (unsigned b = 0; b < blocks; b++)
+        for (unsigned w0 = 0; w0 < threads; w0 += 32) {
+            hostsim_warp ctx;
+            std::vector<std::thread> lanes;
+            for (unsigned t = w0; t < w0 + 32 && t < threads; t++)
+                lanes.emplace_back([&, t] {
+                    gridDim.x = blocks; blockDim.x = threads; blockIdx.x = b; threadIdx.x = t;
+                    hostsim_ctx = &ctx;
+                    body();
+                    hostsim_ctx = nullptr;
+                });
+            for (auto &l : lanes) l.join();
+        }
+}
+
+// per-key tables of `nkeys` keys (key k = item k of qx / qy), built by the product's four kernels; four != 0: the doubling
+// chain by k_kt_bases4 (four lanes per key, in lockstep), else by the one-thread-per-key k_kt_bases.  ktab_out: the final
+// affine tables (KtSizes::ktab_words(nkeys) words), flags_out: nkeys validity flags.
+template <class C, int W>
+static void tables_t(uint32_t nkeys, const uint8_t *qx, const uint8_t *qy, int four, uint32_t *ktab_out, uint8_t *flags_out) {
+    using KS = KtSizes<C, W>;
+    using KT = KeyTab<32 * C::N, W>;
+    const size_t cap = nkeys;
+    std::vector<uint32_t> bases(KS::bases_words(cap)), hs(KS::hs_words(cap)), ztop(KS::ztop_words(cap)), pref(KS::ztop_words(cap)), ktab(KS::ktab_words(cap), 0);
+    std::vector<uint8_t> kflags(cap, 0);
+    uint32_t cnt = nkeys;
+    if (four) run_grid_lockstep((unsigned)((cap * 4 + 127) / 128), 128, [&] { k_kt_bases4<C, W>(&cnt, (uint32_t)cap, nullptr, qx, qy, bases.data(), kflags.data()); });
+    else run_grid((unsigned)((cap + 63) / 64), 64, [&] { k_kt_bases<C, W, true>(&cnt, (uint32_t)cap, nullptr, qx, qy, bases.data(), kflags.data()); });
+    run_grid((unsigned)((cap * KT::NWIN + 63) / 64), 64, [&] { k_kt_fill<C, W>(&cnt, (uint32_t)cap, bases.data(), kflags.data(), hs.data(), ztop.data(), ktab.data()); });
+    run_grid((unsigned)((cap + 63) / 64), 64, [&] { k_kt_inv<C, W>(&cnt, (uint32_t)cap, kflags.data(), ztop.data(), pref.data()); });
+    run_grid((unsigned)((cap * KT::NWIN + 63) / 64), 64, [&] { k_kt_final<C, W>(&cnt, (uint32_t)cap, bases.data(), kflags.data(), hs.data(), ztop.data(), ktab.data()); });
+    memcpy(ktab_out, ktab.data(), ktab.size() * 4);
+    memcpy(flags_out, kflags.data(), cap);
+}
+
+extern "C" size_t hs_ktab_words(int curve, int w8, size_t nkeys) {
+    if (curve == 0) return w8 ? KtSizes<P256, 8>::ktab_words(nkeys) : KtSizes<P256, 5>::ktab_words(nkeys);
+    return w8 ? KtSizes<P384, 8>::ktab_words(nkeys) : KtSizes<P384, 5>::ktab_words(nkeys);
+}
+extern "C" int hs_tables(int curve, int w8, size_t nkeys, const uint8_t *qx, const uint8_t *qy, int four, uint32_t *ktab_out, uint8_t *flags_out) {
+    if (curve == 0 && !w8) tables_t<P256, 5>((uint32_t)nkeys, qx, qy, four, ktab_out, flags_out);
+    else if (curve == 0) tables_t<P256, 8>((uint32_t)nkeys, qx, qy, four, ktab_out, flags_out);
+    else if (!w8) tables_t<P384, 5>((uint32_t)nkeys, qx, qy, four, ktab_out, flags_out);
+    else tables_t<P384, 8>((uint32_t)nkeys, qx, qy, four, ktab_out, flags_out);
     return 0;
 }
 
