@@ -26,6 +26,7 @@ struct hostsim_dim3 { unsigned x = 1, y = 1, z = 1; };
 extern thread_local hostsim_dim3 threadIdx, blockIdx, blockDim, gridDim;
 struct uint4 { uint32_t x, y, z, w; };
 struct uint2 { uint32_t x, y; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 
 template <class T> static inline T __ldg(const T *p) { return *p; }
 static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) {
@@ -89,6 +90,14 @@ static inline unsigned __ballot_sync(unsigned mask, int p) {
     return r;
 }
 static inline unsigned __activemask() { return 1u; }
+static inline unsigned __match_any_sync(unsigned mask, uint32_t v) {
+    if (!hostsim_ctx) return 1u << (threadIdx.x & 31);
+    uint32_t all[32];
+    hostsim_exchange(mask, v, all);
+    unsigned r = 0;
+    for (int i = 0; i < 32; i++) if (((mask >> i) & 1) && all[i] == v) r |= 1u << i;
+    return r;
+}
 template <class T> static inline T __shfl_sync(unsigned mask, T v, int src) {
     static_assert(sizeof(T) == 4, "32-bit shuffles only");
     if (!hostsim_ctx) return v;

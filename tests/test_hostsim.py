@@ -267,3 +267,53 @@ def test_four_lane_doubling_chain_in_lockstep(hs, curve, w8, nkeys):
                 continue
             P = ref.scalar_mult(c, (e << (W * win)) % c.n, Q)
             assert val(tab[win, e - 1, 0]) == P[0] * Rm % c.p and val(tab[win, e - 1, 1]) == P[1] * Rm % c.p, (win, e)
+
+
+@pytest.mark.parametrize("curve,n", [(0, 40), (1, 12)])
+def test_registered_keys_thread_and_warp_kernels(hs, curve, n):
+    """sbv_set_keys / sbv_verify_registered on the CPU: 8-bit-window tables, keys taken by slot, the thread-per-signature
+    kernel and the ONE-SIGNATURE-PER-WARP kernel (32 OS threads per signature, shuffle-tree reduction in lockstep):
+    both equal the oracle, including an invalid registered key and an out-of-range slot."""
+    cv = oracle.P256 if curve == 0 else oracle.P384
+    c = ref.CURVES[cv]
+    L, K = c.size, 4
+    b = corpus.make_batch(cv, n=n, K=K - 1, seed=60 + curve, corrupt_rate=4)
+    d, kxy = corpus.make_keys(cv, K, seed=70 + curve)
+    key_idx = (np.arange(n) % K).astype(np.uint32)
+    r, s = oracle.sign_batch(cv, d, key_idx, b["digest"], corpus._blocks(71, n, L, b"k"))
+    s[::5, L // 2] ^= 4                                          # bad signatures
+    kxy = kxy.copy()
+    kxy[3, L + 3] ^= 8                                           # registered key 3 is not on the curve
+    slot = key_idx.copy()
+    slot[7] = 99                                                 # no such slot
+    qx, qy = np.ascontiguousarray(kxy[key_idx, :L]), np.ascontiguousarray(kxy[key_idx, L:])
+    want = oracle.verify_batch(cv, r, s, qx, qy, b["digest"])
+    want[7] = 0
+    assert want[key_idx == 3].sum() == 0 and 0 < want.sum() < n
+    kx, ky = np.ascontiguousarray(kxy[:, :L]), np.ascontiguousarray(kxy[:, L:])
+    dig = np.ascontiguousarray(b["digest"])
+    for warp in (0, 1):
+        ok = np.full(n, 7, np.uint8)
+        assert hs.hs_verify_registered(C.c_int(curve), C.c_size_t(n), C.c_size_t(K), _p8(kx), _p8(ky), slot.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                       _p8(r), _p8(s), _p8(dig), C.c_uint32(dig.size // n), C.c_int(warp), _p8(ok)) == 0
+        assert np.array_equal(ok, want), (warp, np.nonzero(ok != want)[0])
+
+
+def test_sha256_kernel_on_a_ragged_batch(hs):
+    """k_sha256 (aligned 32-bit loads re-aligned with PRMT, padding built in registers) against hashlib: every length
+    0..200 plus block boundaries, at arbitrary byte offsets, in input order and in a permuted processing order."""
+    import hashlib
+    rng = np.random.default_rng(5)
+    lens = list(range(0, 200)) + [247, 248, 255, 256, 257, 1000, 4095, 4096] + rng.integers(0, 1500, 60).tolist()
+    off = np.zeros(len(lens) + 1, np.uint64)
+    off[1:] = np.cumsum(lens)
+    lead = 3                                                    # the batch does not start on a word boundary
+    off += np.uint64(lead)
+    buf = rng.integers(0, 256, int(off[-1]) + 16, dtype=np.uint8)
+    n = len(lens)
+    want = np.stack([np.frombuffer(hashlib.sha256(buf[int(off[i]):int(off[i + 1])].tobytes()).digest(), np.uint8) for i in range(n)])
+    for perm in (None, rng.permutation(n).astype(np.uint32)):
+        out = np.zeros((n, 32), np.uint8)
+        assert hs.hs_sha256(C.c_size_t(n), _p8(buf), off.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_uint64(0),
+                            None if perm is None else perm.ctypes.data_as(C.POINTER(C.c_uint32)), _p8(out)) == 0
+        assert np.array_equal(out, want)

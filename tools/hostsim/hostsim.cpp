@@ -14,6 +14,7 @@ thread_local hostsim_warp *hostsim_ctx = nullptr;
 namespace sbv { uint32_t tab[1 << 18]; }
 #include "../../consensus_b200/csrc/debug_ops.cuh"
 #include "../../consensus_b200/csrc/keygroup.cuh"
+#include "../../consensus_b200/csrc/sha256.cuh"
 
 using namespace sbv;
 
@@ -117,6 +118,46 @@ extern "C" int hs_tables(int curve, int w8, size_t nkeys, const uint8_t *qx, con
     else if (curve == 0) tables_t<P256, 8>((uint32_t)nkeys, qx, qy, four, ktab_out, flags_out);
     else if (!w8) tables_t<P384, 5>((uint32_t)nkeys, qx, qy, four, ktab_out, flags_out);
     else tables_t<P384, 8>((uint32_t)nkeys, qx, qy, four, ktab_out, flags_out);
+    return 0;
+}
+
+// k_sha256 over a ragged batch, one message per simulated thread (perm: optional processing order, as the counting sort gives it)
+extern "C" int hs_sha256(size_t n, const uint8_t *msgs, const uint64_t *off, uint64_t base, const uint32_t *perm, uint8_t *digest_out) {
+    run_grid((unsigned)((n + 127) / 128), 128, [&] { k_sha256((uint32_t)n, msgs, off, base, digest_out, perm); });
+    return 0;
+}
+
+// registered-key path (sbv_set_keys / sbv_verify_registered): 8-bit window tables for `nkeys` keys, then k_prep and the
+// fixed-base kernel with the key taken by slot — thread per signature, or (warp != 0) ONE SIGNATURE PER WARP in lockstep
+// (k_verify_kt_warp: lanes add their table points, shuffle-tree reduction)
+template <class C>
+static void registered_t(uint32_t n, uint32_t nkeys, const uint8_t *kx, const uint8_t *ky, const uint32_t *slot, const uint8_t *r, const uint8_t *s,
+                         const uint8_t *dig, uint32_t dlen, const uint4 *gtab, int warp, uint8_t *ok) {
+    constexpr int N = C::N, S = 8, W = 8;
+    using KS = KtSizes<C, W>;
+    std::vector<uint32_t> ktab(KS::ktab_words(nkeys));
+    std::vector<uint8_t> kflags(nkeys);
+    tables_t<C, W>(nkeys, kx, ky, 0, ktab.data(), kflags.data());
+    std::vector<int32_t> s2l(nkeys);
+    for (uint32_t i = 0; i < nkeys; i++) s2l[i] = (int32_t)i;
+    std::vector<uint32_t> uw((size_t)2 * N * n);
+    std::vector<uint8_t> flags(n);
+    run_grid(((n + S - 1) / S + 127) / 128, 128, [&] { k_prep<C, S>(n, r, s, dig, dlen, uw.data(), flags.data()); });
+    const uint4 *k4 = reinterpret_cast<const uint4 *>(ktab.data());
+    if (warp)
+        run_grid_lockstep((unsigned)(((size_t)n * 32 + 127) / 128), 128,
+                          [&] { k_verify_kt_warp<C, W>(n, slot, s2l.data(), nkeys, kflags.data(), r, uw.data(), flags.data(), gtab, k4, ok); });
+    else
+        run_grid((n + 63) / 64, 64, [&] {
+            k_verify_kt<C, W, 64, 1, true, false>(n, slot, s2l.data(), nkeys, kflags.data(), r, uw.data(), flags.data(), gtab, k4, ok, nullptr, nullptr, nullptr);
+        });
+}
+
+template <class C> static const uint4 *gtab_for(int idx);
+extern "C" int hs_verify_registered(int curve, size_t n, size_t nkeys, const uint8_t *kx, const uint8_t *ky, const uint32_t *slot, const uint8_t *r,
+                                    const uint8_t *s, const uint8_t *dig, uint32_t dlen, int warp, uint8_t *ok) {
+    if (curve == 0) registered_t<P256>((uint32_t)n, (uint32_t)nkeys, kx, ky, slot, r, s, dig, dlen, gtab_for<P256>(0), warp, ok);
+    else registered_t<P384>((uint32_t)n, (uint32_t)nkeys, kx, ky, slot, r, s, dig, dlen, gtab_for<P384>(1), warp, ok);
     return 0;
 }
 
