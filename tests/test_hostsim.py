@@ -317,3 +317,52 @@ def test_sha256_kernel_on_a_ragged_batch(hs):
         assert hs.hs_sha256(C.c_size_t(n), _p8(buf), off.ctypes.data_as(C.POINTER(C.c_uint64)), C.c_uint64(0),
                             None if perm is None else perm.ctypes.data_as(C.POINTER(C.c_uint32)), _p8(out)) == 0
         assert np.array_equal(out, want)
+
+
+def test_quorum_and_pack_kernels(hs):
+    """k_quorum_count / k_quorum_reached against the oracle's restatement of processCommits (view.go:519-551, util.go:130-143)
+    on a Byzantine vote stream — whole, and as the two shards of a two-device engine (instances split, instance base
+    subtracted) — and k_pack_bits (a warp ballot per 32 verdicts, in lockstep) against the host-side packing."""
+    from consensus_b200 import sharding
+    rng = np.random.default_rng(11)
+    I, NV = 37, 7
+    inst = np.repeat(np.arange(I, dtype=np.uint32), NV)
+    nv = inst.size
+    sender = (np.tile(np.arange(NV), I) + 1).astype(np.uint16)
+    dup = rng.random(nv) < 0.15
+    sender[dup] = np.roll(sender, 1)[dup]                       # duplicate senders: the later vote must not count
+    signer = sender.copy()
+    wrong = rng.random(nv) < 0.1
+    signer[wrong] = (signer[wrong] % NV) + 1                     # signer != sender: never registered (and burns nothing)
+    dm = (rng.random(nv) > 0.1).astype(np.uint8)
+    ok = (rng.random(nv) > 0.2).astype(np.uint8)
+    self_id = (rng.integers(0, NV, I) + 1).astype(np.uint16)     # the counting node's own id per instance
+    thr = 4
+    want_cnt, want_rch = ref.count_commit_votes_batch(inst, sender, signer, dm, ok, I, thr, self_id)
+    p16, p32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint16)), lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+
+    def run(vlo, vhi, ilo, ihi, with_ok=True):
+        cnt, rch = np.zeros(ihi - ilo, np.uint32), np.zeros(ihi - ilo, np.uint8)
+        a = [np.ascontiguousarray(x[vlo:vhi]) for x in (inst, sender, signer, dm, ok)]
+        sid = np.ascontiguousarray(self_id[ilo:ihi])
+        assert hs.hs_quorum(C.c_size_t(vhi - vlo), p32(a[0]), p16(a[1]), p16(a[2]), _p8(a[3]), _p8(a[4]) if with_ok else None, p16(sid),
+                            C.c_uint32(ilo), C.c_size_t(ihi - ilo), C.c_uint32(thr), p32(cnt), _p8(rch)) == 0
+        return cnt, rch
+    cnt, rch = run(0, nv, 0, I)
+    assert np.array_equal(cnt, want_cnt) and np.array_equal(rch, want_rch) and 0 < rch.sum() < I
+    parts = []
+    for g in range(2):                                           # sharded by instance, as sbv_verify_quorum does on two devices
+        ilo, ihi = sharding.shard_range(I, g, 2)
+        vlo, vhi = int(np.searchsorted(inst, ilo)), int(np.searchsorted(inst, ihi))
+        parts.append(run(vlo, vhi, ilo, ihi))
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), want_cnt)
+    # prepares carry no signature (ok == NULL): every registered vote with a matching digest counts
+    cnt_p, _ = run(0, nv, 0, I, with_ok=False)
+    want_p, _ = ref.count_commit_votes_batch(inst, sender, signer, dm, np.ones(nv, np.uint8), I, thr, self_id)
+    assert np.array_equal(cnt_p, want_p)
+    # verdict bytes -> bitmask
+    for n in (1, 31, 32, 33, 1000):
+        v = (rng.random(n) > 0.4).astype(np.uint8)
+        words = np.zeros((n + 31) // 32, np.uint32)
+        assert hs.hs_pack_bits(C.c_size_t(n), _p8(v), p32(words)) == 0
+        assert np.array_equal(words, sharding.pack_bits(v, words.size)), n

@@ -15,6 +15,7 @@ namespace sbv { uint32_t tab[1 << 18]; }
 #include "../../consensus_b200/csrc/debug_ops.cuh"
 #include "../../consensus_b200/csrc/keygroup.cuh"
 #include "../../consensus_b200/csrc/sha256.cuh"
+#include "../../consensus_b200/csrc/quorum.cuh"
 
 using namespace sbv;
 
@@ -124,6 +125,24 @@ extern "C" int hs_tables(int curve, int w8, size_t nkeys, const uint8_t *qx, con
 // k_sha256 over a ragged batch, one message per simulated thread (perm: optional processing order, as the counting sort gives it)
 extern "C" int hs_sha256(size_t n, const uint8_t *msgs, const uint64_t *off, uint64_t base, const uint32_t *perm, uint8_t *digest_out) {
     run_grid((unsigned)((n + 127) / 128), 128, [&] { k_sha256((uint32_t)n, msgs, off, base, digest_out, perm); });
+    return 0;
+}
+
+// quorum counting (k_quorum_count + k_quorum_reached) for the instances [inst_base, inst_base + n_instances), as one device of a
+// sharded engine runs it; ok may be NULL (prepares)
+extern "C" int hs_quorum(size_t n_votes, const uint32_t *instance, const uint16_t *sender, const uint16_t *signer, const uint8_t *digest_match,
+                         const uint8_t *ok, const uint16_t *self_id, uint32_t inst_base, size_t n_instances, uint32_t threshold, uint32_t *valid_count,
+                         uint8_t *reached) {
+    memset(valid_count, 0, n_instances * 4);
+    run_grid((unsigned)((n_votes + 255) / 256), 256, [&] {
+        k_quorum_count((uint32_t)n_votes, instance, sender, signer, digest_match, ok, self_id, inst_base, (uint32_t)n_instances, valid_count);
+    });
+    run_grid((unsigned)((n_instances + 255) / 256), 256, [&] { k_quorum_reached((uint32_t)n_instances, valid_count, threshold, reached); });
+    return 0;
+}
+// k_pack_bits in lockstep (a warp ballot per 32 verdicts)
+extern "C" int hs_pack_bits(size_t n, const uint8_t *ok, uint32_t *mask) {
+    run_grid_lockstep((unsigned)((n + 255) / 256), 256, [&] { k_pack_bits((uint32_t)n, ok, mask); });
     return 0;
 }
 
