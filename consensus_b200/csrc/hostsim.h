@@ -1,6 +1,7 @@
 // hostsim.h — TEST INFRASTRUCTURE ONLY.  Lets the device headers (mp.cuh, curve.cuh, kernels.cuh, keygroup.cuh)
-// compile with plain g++ so that the limb arithmetic, the group law and the thread-per-item kernels can be run
-// one "thread" at a time on the CPU and compared with Python big integers (tests/test_hostsim.py, -m "not gpu").
+// compile with plain g++ so that the limb arithmetic, the group law and the kernels can be run on the CPU — thread-per-item
+// kernels one "thread" at a time, warp-cooperative ones in lockstep (one OS thread per lane) — and compared with Python big
+// integers and the oracle (tests/test_hostsim.py, -m "not gpu").
 // It is never part of libsbv.so: the product has no CPU path.  Only defined when SBV_HOSTSIM is set and the
 // compiler is not nvcc.
 #pragma once

@@ -1,5 +1,6 @@
-"""CPU simulation of the DEVICE code (tools/hostsim: mp.cuh / curve.cuh / kernels.cuh / keygroup.cuh compiled with g++,
-PTX carry-flag primitives emulated, one simulated thread at a time) against Python big integers and the oracle.
+"""CPU simulation of the DEVICE code (tools/hostsim: mp.cuh / curve.cuh / kernels.cuh / keygroup.cuh / sha256.cuh / quorum.cuh
+compiled with g++, PTX carry-flag primitives emulated; thread-per-item kernels one simulated thread at a time,
+warp-cooperative kernels in lockstep with one OS thread per lane) against Python big integers, hashlib and the oracle.
 
 This is how limb-level arithmetic and the kernels' control flow are checked without a GPU; the `-m gpu` tests run the
 same checks on the real thing.  The simulation is test infrastructure — libsbv.so has no CPU path."""
